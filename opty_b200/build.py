@@ -1,0 +1,163 @@
+"""Compilation of the native pieces: the fixed host runtime
+(``libopty_b200.so``) and the per-problem sm_100a modules emitted by
+:mod:`opty_b200.codegen`.
+
+Plays the role of the ``setup.py build_ext --inplace`` subprocess and the
+source-hash module cache of ``ufuncify_matrix`` (opty/utils.py:759-770,
+824-916).  Like the reference, a failed compilation surfaces as an
+``ImportError`` carrying the compiler's stderr (opty/utils.py:909-916).
+"""
+
+import hashlib
+import json
+import logging
+import os
+import shutil
+import subprocess
+import tempfile
+
+logger = logging.getLogger(__name__)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, 'csrc')
+RUNTIME_SRC = os.path.join(CSRC, 'runtime.cu')
+RUNTIME_LIB = os.path.join(_HERE, 'libopty_b200.so')
+INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), 'include')
+
+ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
+
+
+def nvcc_path():
+    for cand in (os.environ.get('OPTY_B200_NVCC'), shutil.which('nvcc'),
+                 '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise ImportError('nvcc was not found; opty_b200 needs the CUDA toolkit '
+                      'to build its sm_100a kernels.')
+
+
+def default_cache_dir():
+    return os.environ.get('OPTY_B200_CACHE', os.path.join(_HERE, '_cache'))
+
+
+def _newer(src_files, target):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in src_files)
+
+
+def build_runtime(force=False, verbose=False):
+    """Builds ``libopty_b200.so`` (in-tree) if it is missing or stale."""
+    deps = [RUNTIME_SRC, os.path.join(CSRC, 'colloc_params.h'),
+            os.path.join(INCLUDE_DIR, 'opty_b200.h')]
+    if not force and not _newer(deps, RUNTIME_LIB):
+        return RUNTIME_LIB
+    cmd = [nvcc_path()] + ARCH_FLAGS + [
+        '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC',
+        '-cudart', 'static', '-o', RUNTIME_LIB, RUNTIME_SRC]
+    logger.info('Building %s', RUNTIME_LIB)
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        print(proc.stdout)
+        print(proc.stderr)
+    if proc.returncode != 0:
+        raise ImportError('Unable to build the opty_b200 runtime library, '
+                          'compilation failed. STDERR output from '
+                          'compilation:\n{}'.format(proc.stderr))
+    return RUNTIME_LIB
+
+
+def _header_digest():
+    hasher = hashlib.sha256()
+    for name in ('colloc_kernel.cuh', 'colloc_params.h'):
+        with open(os.path.join(CSRC, name), 'rb') as f:
+            hasher.update(f.read())
+    return hasher.hexdigest()
+
+
+def module_flags(fmad=False, maxrregcount=None, opt_level=3):
+    flags = ARCH_FLAGS + ['-cubin', '-O{}'.format(opt_level), '-lineinfo',
+                          '-std=c++17',
+                          '--fmad={}'.format('true' if fmad else 'false'),
+                          '-I', CSRC]
+    if maxrregcount:
+        flags += ['-maxrregcount', str(int(maxrregcount))]
+    return flags
+
+
+def compile_module(source, flags, cache_dir=None, show_compile_output=False,
+                   keep_source=True):
+    """Compiles emitted CUDA-C ``source`` to a cubin, with a content-addressed
+    cache (key = sha256 of source + flags + kernel header).
+
+    Returns ``(cubin_bytes, cubin_path, cache_hit)``.
+    """
+    cache_dir = cache_dir or default_cache_dir()
+    hasher = hashlib.sha256()
+    hasher.update(source.encode())
+    hasher.update(' '.join(flags).encode())
+    hasher.update(_header_digest().encode())
+    key = hasher.hexdigest()[:32]
+    os.makedirs(cache_dir, exist_ok=True)
+    cubin_path = os.path.join(cache_dir, 'colloc_{}.cubin'.format(key))
+    if os.path.exists(cubin_path) and os.path.getsize(cubin_path) > 0:
+        logger.info('Skipped compile, %s loaded.', cubin_path)
+        with open(cubin_path, 'rb') as f:
+            return f.read(), cubin_path, True
+
+    src_path = os.path.join(cache_dir, 'colloc_{}.cu'.format(key))
+    with open(src_path, 'w') as f:
+        f.write('// opty_code_hash={}\n'.format(key))
+        f.write(source)
+    tmp_out = tempfile.NamedTemporaryFile(
+        dir=cache_dir, suffix='.cubin.tmp', delete=False)
+    tmp_out.close()
+    cmd = [nvcc_path()] + list(flags) + ['-o', tmp_out.name, src_path]
+    if show_compile_output:
+        cmd.insert(1, '-Xptxas')
+        cmd.insert(2, '-v')
+    logger.info('Compiling the collocation module %s', src_path)
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if show_compile_output:
+        print(proc.stdout)
+        print(proc.stderr)
+    else:
+        logger.debug(proc.stdout)
+        logger.debug(proc.stderr)
+    if proc.returncode != 0 or os.path.getsize(tmp_out.name) == 0:
+        try:
+            os.unlink(tmp_out.name)
+        except OSError:
+            pass
+        raise ImportError(
+            'Unable to compile the generated CUDA module {}, compilation '
+            'failed. STDERR output from compilation:\n{}'.format(
+                src_path, proc.stderr))
+    os.replace(tmp_out.name, cubin_path)
+    if not keep_source:
+        os.unlink(src_path)
+    with open(cubin_path, 'rb') as f:
+        return f.read(), cubin_path, False
+
+
+def load_index(cache_dir, input_key):
+    path = os.path.join(cache_dir or default_cache_dir(),
+                        'index_{}.json'.format(input_key))
+    if not os.path.exists(path):
+        return None
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
+def store_index(cache_dir, input_key, payload):
+    cache_dir = cache_dir or default_cache_dir()
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, 'index_{}.json'.format(input_key))
+    tmp = path + '.tmp{}'.format(os.getpid())
+    with open(tmp, 'w') as f:
+        json.dump(payload, f)
+    os.replace(tmp, path)

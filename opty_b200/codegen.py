@@ -1,0 +1,285 @@
+"""SymPy -> CUDA-C emitter: turns a :class:`CollocationProgram` into the source
+of one sm_100a module.
+
+This is the replacement for the C / Cython text templates of
+``opty.utils.ufuncify_matrix`` (opty/utils.py:483-546, 743-818).  The module
+contains
+
+``opty_colloc_inv``
+    single-thread kernel that evaluates the node-invariant sub-expressions
+    (functions of the parameters and the time interval only) into a table that
+    the host runtime copies to ``__constant__`` memory,
+
+``opty_colloc_eval``
+    the hot kernel: ``grid = (ceil(nodes / (32*W)), groups)``.  A warp owns 32
+    consecutive collocation nodes (lane = node) and one output group (a
+    contiguous range of EOM rows); it stages its slice of the trajectory
+    matrix in shared memory with one TMA tile load, runs the group's
+    straight-line float64 code, writes the residuals eom-major and streams the
+    node-major Jacobian block through a double-buffered shared-memory tile that
+    is drained by TMA tile stores.
+
+The skeleton (staging, tiles, TMA, flush) is hand written in
+``csrc/colloc_kernel.cuh``; only the arithmetic bodies and sizes come from
+here.
+"""
+
+import os
+
+from . import ir
+
+EMITTER_VERSION = 3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+KERNEL_HEADER = os.path.join(_HERE, 'csrc', 'colloc_kernel.cuh')
+
+
+def _lit(v):
+    if v != v:
+        return '__longlong_as_double(0x7ff8000000000000LL)'
+    if v in (float('inf'), float('-inf')):
+        return ('' if v > 0 else '-') + \
+            '__longlong_as_double(0x7ff0000000000000LL)'
+    s = repr(float(v))
+    if 'e' not in s and '.' not in s:
+        s += '.0'
+    return s
+
+
+class _BodyWriter(object):
+    """Emits straight-line code for tape nodes on demand (depth-first from the
+    outputs, so temporaries are defined close to their first use)."""
+
+    def __init__(self, prog, varying_ctx):
+        self.prog = prog
+        self.T = prog.tape
+        self.varying_ctx = varying_ctx   # True: main kernel, False: inv kernel
+        self.done = set()
+        self.lines = []
+        self.num_ops = 0
+
+    def ref(self, i):
+        T = self.T
+        o = T.op[i]
+        if o == ir.CONST:
+            return _lit(T.val[i])
+        if self.varying_ctx:
+            if o == ir.VIN:
+                slot = T.a[i]
+                return '{}({})'.format('XB' if slot & 1 else 'XA', slot >> 1)
+            if not T.varying[i]:
+                return 'CI({})'.format(self.prog.inv_index[i])
+            return 'v{}'.format(i)
+        if o == ir.UIN:
+            return 'uni[{}]'.format(T.a[i])
+        return 'w{}'.format(i)
+
+    def need(self, root):
+        """Makes sure ``root`` (and what it depends on) has been emitted."""
+        T = self.T
+        op_, a_, b_, c_ = T.op, T.a, T.b, T.c
+        varying = T.varying
+        done = self.done
+        vctx = self.varying_ctx
+
+        def is_leaf(i):
+            o = op_[i]
+            if o <= ir.UIN:
+                return True
+            if vctx and not varying[i]:
+                return True
+            return i in done
+
+        if is_leaf(root):
+            return
+        stack = [(root, False)]
+        while stack:
+            i, expanded = stack.pop()
+            if i in done:
+                continue
+            if expanded:
+                self._emit(i)
+                done.add(i)
+                continue
+            stack.append((i, True))
+            # push so that operand ``a`` is emitted first
+            for o in (c_[i], b_[i], a_[i]):
+                if o >= 0 and not is_leaf(o):
+                    stack.append((o, False))
+
+    def _emit(self, i):
+        T = self.T
+        o = T.op[i]
+        r = self.ref
+        a, b, c = T.a[i], T.b[i], T.c[i]
+        name = ('v{}' if self.varying_ctx else 'w{}').format(i)
+        typ = 'const double'
+        if o == ir.NEG:
+            e = '-{}'.format(r(a))
+        elif o == ir.ADD:
+            e = '{} + {}'.format(r(a), r(b))
+        elif o == ir.SUB:
+            e = '{} - {}'.format(r(a), r(b))
+        elif o == ir.MUL:
+            e = '{} * {}'.format(r(a), r(b))
+        elif o == ir.DIV:
+            e = '{} / {}'.format(r(a), r(b))
+        elif o in ir.UNARY_MATH:
+            e = '{}({})'.format(ir.OP_NAMES[o], r(a))
+        elif o in (ir.POW, ir.ATAN2, ir.MIN, ir.MAX):
+            e = '{}({}, {})'.format(ir.OP_NAMES[o], r(a), r(b))
+        elif o == ir.SIGN:
+            e = 'opty_sign({})'.format(r(a))
+        elif o == ir.SEL:
+            e = '({} ? {} : {})'.format(r(a), r(b), r(c))
+        elif o in ir.BOOL_OPS:
+            typ = 'const bool'
+            sym = {ir.LT: '<', ir.LE: '<=', ir.EQ: '==', ir.NE: '!=',
+                   ir.AND: '&&', ir.OR: '||'}
+            if o == ir.NOT:
+                e = '!{}'.format(r(a))
+            else:
+                e = '({} {} {})'.format(r(a), sym[o], r(b))
+        else:
+            raise NotImplementedError(ir.OP_NAMES[o])
+        self.lines.append('{} {} = {};'.format(typ, name, e))
+        self.num_ops += 1
+
+
+def choose_tile_cols(requested):
+    """Tile width C (doubles) of the Jacobian staging tile.  C/2 must be odd
+    so that the 16-byte shared-memory stores of 8 consecutive lanes (row pitch
+    8*C bytes) fall into distinct bank groups."""
+    c = max(2, int(requested))
+    c -= c % 2
+    if (c // 2) % 2 == 0:
+        c -= 2
+    return max(2, c)
+
+
+def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
+                min_blocks_per_sm=4, tma_load=True, tma_store=True):
+    """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
+    (list of ``(r0, r1)`` EOM row ranges)."""
+    T = prog.tape
+    M, P, K, R = prog.M, prog.P, prog.K, prog.R
+    C = choose_tile_cols(tile_cols)
+    ninv = len(prog.inv_nodes)
+
+    out = []
+    w = out.append
+    w('// generated by opty_b200.codegen (emitter v{}); do not edit'.format(
+        EMITTER_VERSION))
+    w('#define OPTY_M {}'.format(M))
+    w('#define OPTY_P {}'.format(P))
+    w('#define OPTY_K {}'.format(K))
+    w('#define OPTY_R {}'.format(R))
+    w('#define OPTY_C {}'.format(C))
+    w('#define OPTY_NGROUPS {}'.format(len(groups)))
+    w('#define OPTY_NINV {}'.format(max(ninv, 1)))
+    w('#define OPTY_NUNI {}'.format(max(prog.num_uniform, 1)))
+    w('#define OPTY_WARPS {}'.format(warps_per_block))
+    w('#define OPTY_MIN_BLOCKS {}'.format(min_blocks_per_sm))
+    w('#define OPTY_TMA_LOAD {}'.format(1 if tma_load else 0))
+    w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
+    w('#include "colloc_kernel.cuh"')
+    w('')
+
+    # ---- invariants kernel -------------------------------------------
+    bw = _BodyWriter(prog, varying_ctx=False)
+    for nid in prog.inv_nodes:
+        bw.need(nid)
+    w('extern "C" __global__ void opty_colloc_inv('
+      'const double* __restrict__ uni, double* __restrict__ inv)')
+    w('{')
+    w('  if (threadIdx.x != 0 || blockIdx.x != 0) return;')
+    for line in bw.lines:
+        w('  ' + line)
+    for k, nid in enumerate(prog.inv_nodes):
+        w('  inv[{}] = {};'.format(k, bw.ref(nid)))
+    w('}')
+    w('')
+    inv_ops = bw.num_ops
+
+    # ---- group bodies --------------------------------------------------
+    group_meta = []
+    for g, (r0, r1) in enumerate(groups):
+        bw = _BodyWriter(prog, varying_ctx=True)
+        body = bw.lines
+        col0 = r0 * P
+        ncols = (r1 - r0) * P
+        w('static __device__ __forceinline__ void opty_group_{}('
+          'const OptyCtx& ctx)'.format(g))
+        w('{')
+        cc = 0          # group-relative column of the next Jacobian entry
+        chunk = 0
+        pending = None  # first half of a 16-byte pair
+
+        def flush(ncols_in_chunk):
+            body.append('OPTY_FLUSH({}, {}, {}, {});'.format(
+                g, chunk, col0, ncols_in_chunk))
+
+        for j in range(r0, r1):
+            bw.need(prog.con[j])
+            body.append('OPTY_CON({}, {});'.format(j, bw.ref(prog.con[j])))
+            for k in range(P):
+                e = prog.jac[j][k]
+                bw.need(e)
+                tc = cc % C
+                if pending is None and tc % 2 == 0 and tc + 1 < C and \
+                        cc + 1 < ncols:
+                    pending = (tc, bw.ref(e))
+                elif pending is not None:
+                    body.append('OPTY_JS2({}, {}, {}, {});'.format(
+                        chunk & 1, pending[0], pending[1], bw.ref(e)))
+                    pending = None
+                else:
+                    body.append('OPTY_JS1({}, {}, {});'.format(
+                        chunk & 1, tc, bw.ref(e)))
+                cc += 1
+                if cc % C == 0 and pending is None:
+                    flush(C)
+                    chunk += 1
+        assert pending is None
+        if cc % C != 0:
+            flush(cc % C)
+            chunk += 1
+        body.append('OPTY_DRAIN();')
+        for line in body:
+            w('  ' + line)
+        w('}')
+        w('')
+        group_meta.append({'rows': [r0, r1], 'col0': col0, 'ncols': ncols,
+                           'ops': bw.num_ops, 'chunks': chunk})
+
+    w('extern "C" __global__ void __launch_bounds__(OPTY_THREADS, '
+      'OPTY_MIN_BLOCKS)')
+    w('opty_colloc_eval(const __grid_constant__ OptyTmaps tm, '
+      'const OptyParams p)')
+    w('{')
+    w('  OPTY_PROLOGUE();')
+    w('  switch (blockIdx.y) {')
+    for g in range(len(groups)):
+        w('    case {}: opty_group_{}(ctx); break;'.format(g, g))
+    w('    default: break;')
+    w('  }')
+    w('}')
+    w('')
+
+    meta = {
+        'emitter_version': EMITTER_VERSION,
+        'M': M, 'P': P, 'K': K, 'R': R, 'C': C,
+        'num_groups': len(groups),
+        'groups': group_meta,
+        'num_inv': ninv,
+        'num_uniform': prog.num_uniform,
+        'inv_ops': inv_ops,
+        'warps_per_block': warps_per_block,
+        'min_blocks_per_sm': min_blocks_per_sm,
+        'tma_load': bool(tma_load),
+        'tma_store': bool(tma_store),
+        'method': method,
+        'entry_kind': prog.entry_kind(),
+        'stats': prog.stats(),
+    }
+    return '\n'.join(out), meta

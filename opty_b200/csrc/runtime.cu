@@ -1,0 +1,601 @@
+// Host runtime behind include/opty_b200.h: owns the device-resident trajectory
+// matrix, the residual / Jacobian buffers, pinned host buffers, the stream and
+// the TMA descriptors, loads the generated sm_100a module and launches it.
+//
+// It replaces the NumPy / Cython glue of the reference's callback path
+// (opty/utils.py:277-326 parse_free, opty/direct_collocation.py:2891-2926
+// _merge_fixed_free, :2382-2446 constraints, :2816-2887 constraints_jacobian)
+// and the Python index loop (opty/direct_collocation.py:2628-2684).
+//
+// Driver-API entry points (module loading, tensor-map encoding, launches) are
+// resolved through cudaGetDriverEntryPoint so that this library has no
+// load-time dependency on libcuda.so.1: it can be dlopen'ed on a machine
+// without a GPU (symbol checks), and fails loudly at opty_colloc_create there.
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/opty_b200.h"
+#include "colloc_params.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define RT_CHECK(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      return fail(OPTY_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorName(e__) + ": " + \
+                                     cudaGetErrorString(e__));                             \
+    }                                                                                      \
+  } while (0)
+
+// ---- driver API, resolved lazily ------------------------------------------
+struct DriverApi {
+  bool ready = false;
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                           unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+};
+
+DriverApi g_drv;
+
+template <typename F>
+int load_entry(const char* name, F* fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || p == nullptr || q != cudaDriverEntryPointSuccess) {
+    return fail(OPTY_ERR_CUDA, std::string("cannot resolve CUDA driver entry point ") + name +
+                                   (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : ""));
+  }
+  *fn = reinterpret_cast<F>(p);
+  return OPTY_OK;
+}
+
+int init_driver() {
+  if (g_drv.ready) return OPTY_OK;
+  int rc;
+  if ((rc = load_entry("cuModuleLoadData", &g_drv.ModuleLoadData))) return rc;
+  if ((rc = load_entry("cuModuleUnload", &g_drv.ModuleUnload))) return rc;
+  if ((rc = load_entry("cuModuleGetFunction", &g_drv.ModuleGetFunction))) return rc;
+  if ((rc = load_entry("cuModuleGetGlobal", &g_drv.ModuleGetGlobal))) return rc;
+  if ((rc = load_entry("cuFuncSetAttribute", &g_drv.FuncSetAttribute))) return rc;
+  if ((rc = load_entry("cuLaunchKernel", &g_drv.LaunchKernel))) return rc;
+  if ((rc = load_entry("cuGetErrorString", &g_drv.GetErrorString))) return rc;
+  if ((rc = load_entry("cuTensorMapEncodeTiled", &g_drv.TensorMapEncodeTiled))) return rc;
+  g_drv.ready = true;
+  return OPTY_OK;
+}
+
+std::string drv_err(CUresult r) {
+  const char* s = nullptr;
+  if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+  return s ? std::string(s) : std::string("CUresult ") + std::to_string((int)r);
+}
+
+#define DRV_CHECK(expr)                                                     \
+  do {                                                                      \
+    CUresult r__ = (expr);                                                  \
+    if (r__ != CUDA_SUCCESS) {                                              \
+      return fail(OPTY_ERR_CUDA, std::string(#expr) + ": " + drv_err(r__)); \
+    }                                                                       \
+  } while (0)
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ---- Jacobian structure kernel ---------------------------------------------
+// One thread per COO entry; entry e of node i, equation j, partial c.  Column
+// formulas are those of opty/direct_collocation.py:2655-2675, row formula of
+// :2644, entry order of :2677-2684.
+__global__ void opty_jac_indices_kernel(long long first, long long count, long long N, long long n,
+                                        long long q, long long M, long long P, int method,
+                                        long long* __restrict__ rows, long long* __restrict__ cols) {
+  const long long MP = M * P;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long e = first + t;
+    const long long i = e / MP;
+    const long long rem = e - i * MP;
+    const long long j = rem / P;
+    const long long c = rem - j * P;
+    long long col;
+    if (method == OPTY_BACKWARD_EULER) {
+      if (c < n) col = c * N + i + 1;
+      else if (c < 2 * n) col = (c - n) * N + i;
+      else if (c < 2 * n + q) col = n * N + (c - 2 * n) * N + i + 1;
+      else col = (n + q) * N + (c - 2 * n - q);
+    } else {
+      if (c < n) col = c * N + i;
+      else if (c < 2 * n) col = (c - n) * N + i + 1;
+      else if (c < 2 * n + q) col = n * N + (c - 2 * n) * N + i;
+      else if (c < 2 * n + 2 * q) col = n * N + (c - 2 * n - q) * N + i + 1;
+      else col = (n + q) * N + (c - 2 * n - 2 * q);
+    }
+    rows[t] = j * (N - 1) + i;
+    cols[t] = col;
+  }
+}
+
+}  // namespace
+
+struct opty_colloc {
+  opty_colloc_cfg cfg;
+  int nn = 0;          // constraint nodes of this handle
+  int ncols = 0;       // trajectory columns held (nn + 1)
+  int R = 0;           // trajectory rows n + q + k
+  int K = 0;           // M * P
+  int64_t ldt = 0;
+  size_t free_len = 0;
+
+  CUmodule mod = nullptr;
+  CUfunction f_eval = nullptr;
+  CUfunction f_inv = nullptr;
+  CUdeviceptr ci_sym = 0;
+  size_t ci_bytes = 0;
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  double* d_traj = nullptr;
+  double* d_uni = nullptr;
+  double* d_inv = nullptr;
+  std::vector<double*> d_con, d_jac;
+  std::vector<std::vector<unsigned char>> tmaps;  // per ring slot: OptyTmaps blob
+  int ring = -1;
+
+  double* h_free = nullptr;    // pinned staging copy of the free vector
+  double* h_shadow = nullptr;  // pageable copy used to detect an unchanged vector
+  double* h_con = nullptr;
+  double* h_jac = nullptr;
+
+  bool known_set = false;
+  bool free_valid = false;
+  bool inv_dirty = true;
+  bool evaluated = false;
+  bool con_fetched = false, jac_fetched = false;
+
+  std::vector<int32_t> d2h_begin, d2h_end;
+  unsigned smem_bytes = 0;
+  unsigned grid_x = 0;
+  int64_t launches = 0;
+  float last_ms = 0.f;
+  bool have_ms = false;
+};
+
+namespace {
+
+int encode_2d(CUtensorMap* map, void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+              uint32_t box0, uint32_t box1) {
+  cuuint64_t gdim[2] = {dim0, dim1};
+  cuuint64_t gstr[1] = {stride1_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  DRV_CHECK(g_drv.TensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+  return OPTY_OK;
+}
+
+int build_tmaps(opty_colloc* h, int slot) {
+  const opty_colloc_cfg& c = h->cfg;
+  std::vector<unsigned char>& blob = h->tmaps[slot];
+  blob.assign(sizeof(CUtensorMap) * (1 + c.num_groups), 0);
+  CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(blob.data());
+  int rc;
+  if (c.tma_load) {
+    const uint32_t xw = 32u * c.warps_per_block + 2u;
+    if ((rc = encode_2d(&maps[0], h->d_traj, (uint64_t)h->ncols, (uint64_t)h->R, (uint64_t)h->ldt * 8, xw,
+                        (uint32_t)h->R)))
+      return rc;
+  }
+  if (c.tma_store) {
+    for (int g = 0; g < c.num_groups; ++g) {
+      if ((rc = encode_2d(&maps[1 + g], h->d_jac[slot] + c.group_col0[g], (uint64_t)c.group_ncols[g],
+                          (uint64_t)h->nn, (uint64_t)h->K * 8, (uint32_t)c.tile_cols, 32u)))
+        return rc;
+    }
+  }
+  return OPTY_OK;
+}
+
+int launch_eval(opty_colloc* h) {
+  const opty_colloc_cfg& c = h->cfg;
+  if (!h->known_set) return fail(OPTY_ERR_STATE, "opty_colloc_set_known must be called before evaluating");
+  if (!h->free_valid) return fail(OPTY_ERR_STATE, "no free vector resident on the device");
+  RT_CHECK(cudaEventRecord(h->ev0, h->stream));
+  if (h->inv_dirty && c.num_inv > 0) {
+    void* args[2] = {&h->d_uni, &h->d_inv};
+    DRV_CHECK(g_drv.LaunchKernel(h->f_inv, 1, 1, 1, 32, 1, 1, 0, (CUstream)h->stream, args, nullptr));
+    h->launches++;
+    RT_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(h->ci_sym), h->d_inv, (size_t)c.num_inv * 8,
+                             cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->inv_dirty = false;
+  h->ring = (h->ring + 1) % c.out_ring;
+  OptyParams p;
+  p.traj = h->d_traj;
+  p.con = h->d_con[h->ring];
+  p.jac = h->d_jac[h->ring];
+  p.ldt = h->ldt;
+  p.ldc = h->nn;
+  p.n_nodes = h->nn;
+  p.n_cols = h->ncols;
+  void* args[2] = {h->tmaps[h->ring].data(), &p};
+  DRV_CHECK(g_drv.LaunchKernel(h->f_eval, h->grid_x, (unsigned)c.num_groups, 1, 32u * c.warps_per_block, 1, 1,
+                               h->smem_bytes, (CUstream)h->stream, args, nullptr));
+  h->launches++;
+  RT_CHECK(cudaEventRecord(h->ev1, h->stream));
+  h->have_ms = true;
+  h->evaluated = true;
+  h->con_fetched = h->jac_fetched = false;
+  return OPTY_OK;
+}
+
+int upload(opty_colloc* h, const double* free_host, bool* changed_out) {
+  const opty_colloc_cfg& c = h->cfg;
+  const size_t bytes = h->free_len * 8;
+  bool changed = !h->free_valid || memcmp(free_host, h->h_shadow, bytes) != 0;
+  if (changed_out) *changed_out = changed;
+  if (!changed) return OPTY_OK;
+  memcpy(h->h_shadow, free_host, bytes);
+  if (free_host != h->h_free) memcpy(h->h_free, free_host, bytes);
+  const int rows = c.n + c.q;
+  // rows of the free vector are [row][N]; this handle keeps columns node_lo..node_hi
+  RT_CHECK(cudaMemcpy2DAsync(h->d_traj, (size_t)h->ldt * 8, h->h_free + c.node_lo, (size_t)c.N * 8,
+                             (size_t)h->ncols * 8, rows, cudaMemcpyHostToDevice, h->stream));
+  if (c.r + c.s > 0) {
+    RT_CHECK(cudaMemcpyAsync(h->d_uni + c.pk, h->h_free + (size_t)rows * c.N, (size_t)(c.r + c.s) * 8,
+                             cudaMemcpyHostToDevice, h->stream));
+    h->inv_dirty = true;
+  }
+  h->free_valid = true;
+  h->evaluated = false;
+  return OPTY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* opty_colloc_last_error(void) { return g_err.c_str(); }
+
+int opty_b200_abi_version(void) { return OPTY_B200_ABI_VERSION; }
+
+int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cubin_bytes, opty_colloc_t** out) {
+  if (!cfg || !cubin || !out || cubin_bytes == 0) return fail(OPTY_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != OPTY_B200_ABI_VERSION) return fail(OPTY_ERR_ARG, "ABI version mismatch");
+  if (cfg->N < 2 || cfg->n < 1 || cfg->M < 1 || cfg->P < 1 || cfg->q < 0 || cfg->k < 0 || cfg->r < 0 ||
+      cfg->pk < 0 || (cfg->s != 0 && cfg->s != 1))
+    return fail(OPTY_ERR_ARG, "invalid problem dimensions");
+  if (cfg->node_lo < 0 || cfg->node_hi > cfg->N - 1 || cfg->node_lo >= cfg->node_hi)
+    return fail(OPTY_ERR_ARG, "invalid node range");
+  if (cfg->num_groups < 1 || cfg->num_groups > OPTY_MAX_GROUPS) return fail(OPTY_ERR_ARG, "invalid group count");
+  if (cfg->warps_per_block < 1 || cfg->warps_per_block > 32 || cfg->tile_cols < 2 || (cfg->tile_cols & 1) ||
+      cfg->tile_cols > 256)
+    return fail(OPTY_ERR_ARG, "invalid kernel geometry");
+  if (cfg->out_ring < 1 || cfg->out_ring > 64) return fail(OPTY_ERR_ARG, "invalid out_ring");
+  const int expectP = (cfg->method == OPTY_MIDPOINT ? 2 * cfg->n + 2 * cfg->q : 2 * cfg->n + cfg->q) + cfg->r + cfg->s;
+  if (cfg->method != OPTY_MIDPOINT && cfg->method != OPTY_BACKWARD_EULER) return fail(OPTY_ERR_ARG, "invalid method");
+  if (cfg->P != expectP) return fail(OPTY_ERR_ARG, "P does not match n, q, r, s and the integration method");
+  {
+    long long covered = 0;
+    for (int g = 0; g < cfg->num_groups; ++g) {
+      if (cfg->group_col0[g] != covered || cfg->group_ncols[g] < 1) return fail(OPTY_ERR_ARG, "groups must tile the K columns");
+      covered += cfg->group_ncols[g];
+    }
+    if (covered != (long long)cfg->M * cfg->P) return fail(OPTY_ERR_ARG, "groups must tile the K columns");
+  }
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(OPTY_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(OPTY_ERR_ARG, "invalid device ordinal");
+  RT_CHECK(cudaSetDevice(cfg->device));
+  RT_CHECK(cudaFree(0));
+  int rc = init_driver();
+  if (rc) return rc;
+
+  opty_colloc* h = new opty_colloc();
+  h->cfg = *cfg;
+  h->nn = cfg->node_hi - cfg->node_lo;
+  h->ncols = h->nn + 1;
+  h->R = cfg->n + cfg->q + cfg->k;
+  h->K = cfg->M * cfg->P;
+  h->ldt = round_up(h->ncols, 16);
+  h->free_len = (size_t)(cfg->n + cfg->q) * cfg->N + cfg->r + cfg->s;
+  if (cfg->tma_load && h->R > 256) {
+    delete h;
+    return fail(OPTY_ERR_ARG, "TMA input staging supports at most 256 trajectory rows");
+  }
+  if (cfg->tma_store && ((h->K & 1) != 0)) {
+    delete h;
+    return fail(OPTY_ERR_ARG, "TMA Jacobian stores need an even M*P");
+  }
+
+#define CREATE_CHECK(stmt)        \
+  do {                            \
+    int rc__ = (stmt);            \
+    if (rc__) {                   \
+      opty_colloc_destroy(h);     \
+      return rc__;                \
+    }                             \
+  } while (0)
+#define CREATE_RT(expr) CREATE_CHECK([&]() -> int { RT_CHECK(expr); return OPTY_OK; }())
+#define CREATE_DRV(expr) CREATE_CHECK([&]() -> int { DRV_CHECK(expr); return OPTY_OK; }())
+
+  CREATE_DRV(g_drv.ModuleLoadData(&h->mod, cubin));
+  CREATE_DRV(g_drv.ModuleGetFunction(&h->f_eval, h->mod, "opty_colloc_eval"));
+  CREATE_DRV(g_drv.ModuleGetFunction(&h->f_inv, h->mod, "opty_colloc_inv"));
+  CREATE_DRV(g_drv.ModuleGetGlobal(&h->ci_sym, &h->ci_bytes, h->mod, "opty_ci"));
+  if (h->ci_bytes < (size_t)cfg->num_inv * 8) {
+    opty_colloc_destroy(h);
+    return fail(OPTY_ERR_ARG, "module's invariant table is smaller than cfg.num_inv");
+  }
+
+  CREATE_RT(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_RT(cudaEventCreate(&h->ev0));
+  CREATE_RT(cudaEventCreate(&h->ev1));
+
+  CREATE_RT(cudaMalloc(&h->d_traj, (size_t)h->R * h->ldt * 8));
+  CREATE_RT(cudaMemsetAsync(h->d_traj, 0, (size_t)h->R * h->ldt * 8, h->stream));
+  const int nuni = cfg->pk + cfg->r + 1;
+  CREATE_RT(cudaMalloc(&h->d_uni, (size_t)nuni * 8));
+  CREATE_RT(cudaMemsetAsync(h->d_uni, 0, (size_t)nuni * 8, h->stream));
+  if (cfg->s == 0) {
+    CREATE_RT(cudaMemcpyAsync(h->d_uni + cfg->pk + cfg->r, &cfg->h, 8, cudaMemcpyHostToDevice, h->stream));
+    CREATE_RT(cudaStreamSynchronize(h->stream));
+  }
+  CREATE_RT(cudaMalloc(&h->d_inv, (size_t)(cfg->num_inv > 0 ? cfg->num_inv : 1) * 8));
+  h->d_con.assign(cfg->out_ring, nullptr);
+  h->d_jac.assign(cfg->out_ring, nullptr);
+  h->tmaps.resize(cfg->out_ring);
+  for (int s = 0; s < cfg->out_ring; ++s) {
+    CREATE_RT(cudaMalloc(&h->d_con[s], (size_t)cfg->M * h->nn * 8));
+    CREATE_RT(cudaMalloc(&h->d_jac[s], (size_t)h->nn * h->K * 8));
+    CREATE_CHECK(build_tmaps(h, s));
+  }
+
+  CREATE_RT(cudaHostAlloc(&h->h_free, h->free_len * 8, cudaHostAllocDefault));
+  h->h_shadow = static_cast<double*>(malloc(h->free_len * 8));
+  if (!h->h_shadow) {
+    opty_colloc_destroy(h);
+    return fail(OPTY_ERR_ARG, "out of host memory");
+  }
+  CREATE_RT(cudaHostAlloc(&h->h_con, ((size_t)cfg->M * h->nn + cfg->con_tail) * 8, cudaHostAllocDefault));
+  CREATE_RT(cudaHostAlloc(&h->h_jac, ((size_t)h->nn * h->K + cfg->jac_tail) * 8, cudaHostAllocDefault));
+
+  const unsigned tiles_bytes = (unsigned)cfg->warps_per_block * 2u * 32u * cfg->tile_cols * 8u;
+  const unsigned xw = 32u * cfg->warps_per_block + 2u;
+  const unsigned xin_bytes = (unsigned)round_up((int64_t)h->R * xw * 8, 128);
+  h->smem_bytes = tiles_bytes + xin_bytes + 128u;
+  if (h->smem_bytes > 227u * 1024u) {
+    opty_colloc_destroy(h);
+    return fail(OPTY_ERR_ARG, "kernel needs more than 227 KB of shared memory per block");
+  }
+  CREATE_DRV(g_drv.FuncSetAttribute(h->f_eval, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)h->smem_bytes));
+  h->grid_x = (unsigned)((h->nn + 32 * cfg->warps_per_block - 1) / (32 * cfg->warps_per_block));
+  CREATE_RT(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return OPTY_OK;
+}
+
+int opty_colloc_destroy(opty_colloc_t* h) {
+  if (!h) return OPTY_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (double* p : h->d_con) cudaFree(p);
+  for (double* p : h->d_jac) cudaFree(p);
+  cudaFree(h->d_traj);
+  cudaFree(h->d_uni);
+  cudaFree(h->d_inv);
+  if (h->h_free) cudaFreeHost(h->h_free);
+  if (h->h_con) cudaFreeHost(h->h_con);
+  if (h->h_jac) cudaFreeHost(h->h_jac);
+  free(h->h_shadow);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(h->mod);
+  delete h;
+  return OPTY_OK;
+}
+
+int opty_colloc_set_known(opty_colloc_t* h, const double* traj, const double* params) {
+  if (!h) return fail(OPTY_ERR_ARG, "null handle");
+  const opty_colloc_cfg& c = h->cfg;
+  if ((c.k > 0 && !traj) || (c.pk > 0 && !params)) return fail(OPTY_ERR_ARG, "known values missing");
+  RT_CHECK(cudaSetDevice(c.device));
+  if (c.k > 0) {
+    RT_CHECK(cudaMemcpy2DAsync(h->d_traj + (size_t)(c.n + c.q) * h->ldt, (size_t)h->ldt * 8, traj + c.node_lo,
+                               (size_t)c.N * 8, (size_t)h->ncols * 8, c.k, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (c.pk > 0) {
+    RT_CHECK(cudaMemcpyAsync(h->d_uni, params, (size_t)c.pk * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  RT_CHECK(cudaStreamSynchronize(h->stream));
+  h->known_set = true;
+  h->inv_dirty = true;
+  h->evaluated = false;
+  return OPTY_OK;
+}
+
+int opty_colloc_upload_free(opty_colloc_t* h, const double* free_host) {
+  if (!h || !free_host) return fail(OPTY_ERR_ARG, "null argument");
+  RT_CHECK(cudaSetDevice(h->cfg.device));
+  int rc = upload(h, free_host, nullptr);
+  if (rc) return rc;
+  RT_CHECK(cudaStreamSynchronize(h->stream));
+  return OPTY_OK;
+}
+
+int opty_colloc_eval_device(opty_colloc_t* h, int sync) {
+  if (!h) return fail(OPTY_ERR_ARG, "null handle");
+  RT_CHECK(cudaSetDevice(h->cfg.device));
+  int rc = launch_eval(h);
+  if (rc) return rc;
+  if (sync) RT_CHECK(cudaStreamSynchronize(h->stream));
+  return OPTY_OK;
+}
+
+int opty_colloc_constraints(opty_colloc_t* h, const double* free_host, double* con_host) {
+  if (!h || !free_host) return fail(OPTY_ERR_ARG, "null argument");
+  RT_CHECK(cudaSetDevice(h->cfg.device));
+  int rc = upload(h, free_host, nullptr);
+  if (rc) return rc;
+  if (!h->evaluated && (rc = launch_eval(h))) return rc;
+  const size_t bytes = (size_t)h->cfg.M * h->nn * 8;
+  if (!h->con_fetched) {
+    RT_CHECK(cudaMemcpyAsync(h->h_con, h->d_con[h->ring], bytes, cudaMemcpyDeviceToHost, h->stream));
+    RT_CHECK(cudaStreamSynchronize(h->stream));
+    h->con_fetched = true;
+  }
+  if (con_host && con_host != h->h_con) memcpy(con_host, h->h_con, bytes);
+  return OPTY_OK;
+}
+
+int opty_colloc_jacobian(opty_colloc_t* h, const double* free_host, double* jac_host) {
+  if (!h || !free_host) return fail(OPTY_ERR_ARG, "null argument");
+  RT_CHECK(cudaSetDevice(h->cfg.device));
+  int rc = upload(h, free_host, nullptr);
+  if (rc) return rc;
+  if (!h->evaluated && (rc = launch_eval(h))) return rc;
+  const size_t bytes = (size_t)h->nn * h->K * 8;
+  if (!h->jac_fetched) {
+    if (h->d2h_begin.empty()) {
+      RT_CHECK(cudaMemcpyAsync(h->h_jac, h->d_jac[h->ring], bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      for (size_t i = 0; i < h->d2h_begin.size(); ++i) {
+        const int b = h->d2h_begin[i], e = h->d2h_end[i];
+        RT_CHECK(cudaMemcpy2DAsync(h->h_jac + b, (size_t)h->K * 8, h->d_jac[h->ring] + b, (size_t)h->K * 8,
+                                   (size_t)(e - b) * 8, h->nn, cudaMemcpyDeviceToHost, h->stream));
+      }
+    }
+    RT_CHECK(cudaStreamSynchronize(h->stream));
+    h->jac_fetched = true;
+  }
+  if (jac_host && jac_host != h->h_jac) memcpy(jac_host, h->h_jac, bytes);
+  return OPTY_OK;
+}
+
+int opty_colloc_host_buffers(opty_colloc_t* h, double** free_pinned, double** con_pinned, double** jac_pinned) {
+  if (!h) return fail(OPTY_ERR_ARG, "null handle");
+  if (free_pinned) *free_pinned = h->h_free;
+  if (con_pinned) *con_pinned = h->h_con;
+  if (jac_pinned) *jac_pinned = h->h_jac;
+  return OPTY_OK;
+}
+
+int opty_colloc_device_buffers(opty_colloc_t* h, void** traj, int64_t* ldt, void** con, void** jac, void** uni) {
+  if (!h) return fail(OPTY_ERR_ARG, "null handle");
+  const int slot = h->ring < 0 ? 0 : h->ring;
+  if (traj) *traj = h->d_traj;
+  if (ldt) *ldt = h->ldt;
+  if (con) *con = h->d_con[slot];
+  if (jac) *jac = h->d_jac[slot];
+  if (uni) *uni = h->d_uni;
+  return OPTY_OK;
+}
+
+int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t* col_begin, const int32_t* col_end,
+                                const double* fill) {
+  if (!h || num_ranges < 0) return fail(OPTY_ERR_ARG, "invalid argument");
+  std::vector<int32_t> b, e;
+  int prev = 0;
+  for (int i = 0; i < num_ranges; ++i) {
+    if (!col_begin || !col_end || col_begin[i] < prev || col_end[i] <= col_begin[i] || col_end[i] > h->K)
+      return fail(OPTY_ERR_ARG, "column ranges must be sorted, non-empty and inside [0, M*P)");
+    b.push_back(col_begin[i]);
+    e.push_back(col_end[i]);
+    prev = col_end[i];
+  }
+  if (fill) {
+    // pre-write the per-node constant pattern once
+    for (int64_t i = 0; i < h->nn; ++i) memcpy(h->h_jac + i * h->K, fill, (size_t)h->K * 8);
+  }
+  h->d2h_begin.swap(b);
+  h->d2h_end.swap(e);
+  h->jac_fetched = false;
+  return OPTY_OK;
+}
+
+int opty_colloc_last_kernel_ms(opty_colloc_t* h, float* ms) {
+  if (!h || !ms) return fail(OPTY_ERR_ARG, "null argument");
+  if (!h->have_ms) return fail(OPTY_ERR_STATE, "no evaluation has been launched yet");
+  RT_CHECK(cudaEventSynchronize(h->ev1));
+  RT_CHECK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return OPTY_OK;
+}
+
+int opty_colloc_launch_count(opty_colloc_t* h, int64_t* count) {
+  if (!h || !count) return fail(OPTY_ERR_ARG, "null argument");
+  *count = h->launches;
+  return OPTY_OK;
+}
+
+int opty_colloc_jacobian_indices(int device, int N, int node_lo, int node_hi, int n, int q, int r, int s, int M,
+                                 int method, int64_t* rows, int64_t* cols) {
+  if (!rows || !cols) return fail(OPTY_ERR_ARG, "null argument");
+  if (N < 2 || node_lo < 0 || node_hi > N - 1 || node_lo >= node_hi || n < 1 || q < 0 || r < 0 || s < 0 || M < 1)
+    return fail(OPTY_ERR_ARG, "invalid dimensions");
+  if (method != OPTY_MIDPOINT && method != OPTY_BACKWARD_EULER) return fail(OPTY_ERR_ARG, "invalid method");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(OPTY_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e));
+  RT_CHECK(cudaSetDevice(device));
+  const long long P = (method == OPTY_MIDPOINT ? 2LL * n + 2LL * q : 2LL * n + q) + r + s;
+  const long long MP = (long long)M * P;
+  const long long first = (long long)node_lo * MP;
+  const long long total = (long long)(node_hi - node_lo) * MP;
+  const long long chunk = 1LL << 25;  // 32 Mi entries = 2 x 256 MiB of int64 per pass
+  long long *d_rows = nullptr, *d_cols = nullptr;
+  const long long cap = total < chunk ? total : chunk;
+  RT_CHECK(cudaMalloc(&d_rows, (size_t)cap * 8));
+  cudaError_t e2 = cudaMalloc(&d_cols, (size_t)cap * 8);
+  if (e2 != cudaSuccess) {
+    cudaFree(d_rows);
+    return fail(OPTY_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e2));
+  }
+  int rc = OPTY_OK;
+  for (long long done = 0; done < total && rc == OPTY_OK; done += cap) {
+    const long long cnt = (total - done) < cap ? (total - done) : cap;
+    const int threads = 256;
+    long long blocks = (cnt + threads - 1) / threads;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    opty_jac_indices_kernel<<<(unsigned)blocks, threads>>>(first + done, cnt, N, n, q, M, P, method, d_rows, d_cols);
+    cudaError_t ek = cudaGetLastError();
+    if (ek == cudaSuccess) ek = cudaMemcpy(rows + done, d_rows, (size_t)cnt * 8, cudaMemcpyDeviceToHost);
+    if (ek == cudaSuccess) ek = cudaMemcpy(cols + done, d_cols, (size_t)cnt * 8, cudaMemcpyDeviceToHost);
+    if (ek != cudaSuccess) rc = fail(OPTY_ERR_CUDA, std::string("jacobian_indices: ") + cudaGetErrorString(ek));
+  }
+  cudaFree(d_rows);
+  cudaFree(d_cols);
+  return rc;
+}
+
+}  // extern "C"

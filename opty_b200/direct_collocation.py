@@ -1,0 +1,893 @@
+"""``Problem`` / ``ConstraintCollocator`` with the constructor signatures and
+the cyipopt callback surface of ``opty.direct_collocation`` (reference
+opty/direct_collocation.py:93-567 and :1379-3015), evaluated by generated
+sm_100a CUDA kernels instead of generated C + Cython.
+
+Only the collocation hot path is implemented natively here: symbolic
+transcription -> CUDA-C emitter -> kernels for the constraint residuals and the
+Jacobian partials -> COO structure.  Plotting and initial-guess helpers of the
+reference's ``Problem`` are outside the scope of this package.
+"""
+
+import logging
+import os
+
+import numpy as np
+import sympy as sm
+import sympy.physics.mechanics as me
+from sympy.core.function import AppliedUndef
+
+from . import build, codegen, runtime
+from .program import CollocationProgram
+from .utils import parse_free, sort_sympy
+
+try:  # IPOPT is optional: every callback works without it, only solve() needs it
+    import cyipopt
+    _IpoptBase = cyipopt.Problem
+except ImportError:  # pragma: no cover - depends on the environment
+    cyipopt = None
+
+    class _IpoptBase(object):
+        """Stand-in base class used when cyipopt is not installed."""
+
+        def __init__(self, n=None, m=None, lb=None, ub=None, cl=None, cu=None):
+            self._nlp_dims = (n, m)
+            self._nlp_options = {}
+
+        def add_option(self, name, value):
+            self._nlp_options[name] = value
+
+        def solve(self, *args, **kwargs):
+            raise ImportError('cyipopt (IPOPT) is not installed; the NLP '
+                              'callbacks are available but solve() is not.')
+
+__all__ = ['Problem', 'ConstraintCollocator']
+
+logger = logging.getLogger(__name__)
+
+_METHODS = ('backward euler', 'midpoint')
+
+DEFAULT_CUDA_OPTIONS = {
+    'groups': 'auto',           # number of output groups (grid.y) or 'auto'
+    'tile_cols': 30,            # Jacobian staging tile width (doubles)
+    'warps_per_block': 2,
+    'min_blocks_per_sm': 4,
+    'fmad': False,              # keep mul/add unfused like gcc -O2 on x86-64
+    'maxrregcount': None,
+    'tma_load': True,
+    'tma_store': True,
+    'out_ring': 1,              # device output sets to rotate through
+    'use_sympy_cse': True,
+    'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
+    'target_warps': 148 * 16,
+    'max_group_cost': 6000.0,
+}
+
+
+def _is_callable_value(v):
+    return callable(v) and not isinstance(v, np.ndarray)
+
+
+class ConstraintCollocator(object):
+    """Generates the constraint function, its sparse Jacobian and the
+    Jacobian's COO structure for a direct collocation NLP.
+
+    Notation (reference opty/direct_collocation.py:1385-1398): N nodes, M
+    equations of motion, n states, q unknown and k known input trajectories,
+    r unknown parameters, s = 1 for a free node time interval, o instance
+    constraints.  ``free`` has ``n*N + q*N + r + s`` entries, there are
+    ``M*(N-1) + o`` constraints.
+
+    The constructor takes the reference's arguments in the reference's order
+    (opty/direct_collocation.py:1406-1411); ``parallel`` is accepted and
+    ignored (the CUDA grid is the node loop), ``tmp_dir`` selects the
+    directory of the compiled-module cache.
+
+    Additional keyword arguments
+    ----------------------------
+    backend : 'cuda'
+    device : int, CUDA device ordinal (default ``LOCAL_RANK`` or 0)
+    node_range : (lo, hi), evaluate only constraint nodes ``lo <= i < hi`` of
+        the ``N - 1`` (used for sharding the nodes over several GPUs)
+    cuda_options : dict overriding ``DEFAULT_CUDA_OPTIONS``
+    """
+
+    def __init__(self, equations_of_motion, state_symbols,
+                 num_collocation_nodes, node_time_interval,
+                 known_parameter_map={}, known_trajectory_map={},
+                 instance_constraints=None, time_symbol=None, tmp_dir=None,
+                 integration_method='backward euler', parallel=False,
+                 show_compile_output=False, backend='cuda', device=None,
+                 node_range=None, cuda_options=None):
+        self._eom = equations_of_motion
+
+        # the reference also redirects the global default time symbol
+        # (opty/direct_collocation.py:1490-1494)
+        if time_symbol is None:
+            self._time_symbol = me.dynamicsymbols._t
+        else:
+            self._time_symbol = time_symbol
+            me.dynamicsymbols._t = time_symbol
+
+        self._state_symbols = tuple(state_symbols)
+        if len(set(self._state_symbols)) != len(self._state_symbols):
+            raise ValueError('State symbols must be unique.')
+
+        if backend in ('cython', 'numpy'):
+            raise NotImplementedError(
+                'opty_b200 only ships the "cuda" backend; the "{}" backend '
+                'belongs to the reference implementation.'.format(backend))
+        if backend != 'cuda':
+            raise ValueError('backend must be "cuda".')
+        self._backend = backend
+
+        self._state_derivative_symbols = tuple(
+            s.diff(self._time_symbol) for s in self._state_symbols)
+        self._num_collocation_nodes = int(num_collocation_nodes)
+
+        self._node_time_interval = node_time_interval
+        if isinstance(node_time_interval, sm.Symbol):
+            self._variable_duration = True
+            self._time_interval_symbol = node_time_interval
+        else:
+            self._variable_duration = False
+            self._time_interval_symbol = sm.Symbol('h_opty', real=True)
+
+        self._known_parameter_map = known_parameter_map
+        self._known_trajectory_map = known_trajectory_map
+        self._instance_constraints = instance_constraints
+        self._tmp_dir = tmp_dir
+        self._parallel = parallel
+        self._show_compile_output = show_compile_output
+
+        opts = dict(DEFAULT_CUDA_OPTIONS)
+        if cuda_options:
+            unknown = set(cuda_options) - set(opts)
+            if unknown:
+                raise ValueError('Unknown cuda_options: {}'.format(
+                    sorted(unknown)))
+            opts.update(cuda_options)
+        self._cuda_options = opts
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', 0))
+        self._device = int(device)
+
+        N = self._num_collocation_nodes
+        if node_range is None:
+            node_range = (0, N - 1)
+        lo, hi = int(node_range[0]), int(node_range[1])
+        if not (0 <= lo < hi <= N - 1):
+            raise ValueError('node_range must satisfy 0 <= lo < hi <= N - 1.')
+        self._node_range = (lo, hi)
+
+        self._classify_parameters()
+        self._classify_trajectories()
+        self._num_free = ((self.num_states +
+                           self.num_unknown_input_trajectories) * N +
+                          self.num_unknown_parameters +
+                          int(self._variable_duration))
+        self._check_known_trajectories()
+
+        if integration_method not in _METHODS:
+            raise ValueError('{} is not a valid integration method.'.format(
+                integration_method))
+        self._integration_method = integration_method
+        self._make_discrete_symbols()
+        self._discretize_eom()
+
+        self._num_constraints = self.num_eom * (N - 1)
+        if instance_constraints is None:
+            self._num_instance_constraints = 0
+        else:
+            self._num_instance_constraints = len(instance_constraints)
+            self._num_constraints += self._num_instance_constraints
+            self._index_instance_constraints()
+            self.eval_instance_constraints = \
+                self._instance_constraints_func()
+            self.eval_instance_constraints_jacobian_values = \
+                self._instance_constraints_jacobian_values_func()
+
+        self._evaluator = None
+
+    # ------------------------------------------------------------------
+    # read-only attributes, same names as the reference
+    # (opty/direct_collocation.py:1556-1892)
+    # ------------------------------------------------------------------
+    eom = property(lambda self: self._eom)
+    discrete_eom = property(lambda self: self._discrete_eom)
+    state_symbols = property(lambda self: self._state_symbols)
+    state_derivative_symbols = property(
+        lambda self: self._state_derivative_symbols)
+    time_symbol = property(lambda self: self._time_symbol)
+    time_interval_symbol = property(lambda self: self._time_interval_symbol)
+    node_time_interval = property(lambda self: self._node_time_interval)
+    num_collocation_nodes = property(
+        lambda self: self._num_collocation_nodes)
+    num_constraints = property(lambda self: self._num_constraints)
+    num_free = property(lambda self: self._num_free)
+    num_eom = property(lambda self: self._eom.shape[0])
+    num_states = property(lambda self: len(self._state_symbols))
+    num_instance_constraints = property(
+        lambda self: self._num_instance_constraints)
+    instance_constraints = property(lambda self: self._instance_constraints)
+    integration_method = property(lambda self: self._integration_method)
+    known_parameter_map = property(lambda self: self._known_parameter_map)
+    known_trajectory_map = property(lambda self: self._known_trajectory_map)
+    known_parameters = property(lambda self: self._known_parameters)
+    unknown_parameters = property(lambda self: self._unknown_parameters)
+    parameters = property(lambda self: self._parameters)
+    num_known_parameters = property(lambda self: len(self._known_parameters))
+    num_unknown_parameters = property(
+        lambda self: len(self._unknown_parameters))
+    num_parameters = property(lambda self: len(self._parameters))
+    known_input_trajectories = property(
+        lambda self: self._known_input_trajectories)
+    unknown_input_trajectories = property(
+        lambda self: self._unknown_input_trajectories)
+    input_trajectories = property(lambda self: self._input_trajectories)
+    num_known_input_trajectories = property(
+        lambda self: len(self._known_input_trajectories))
+    num_unknown_input_trajectories = property(
+        lambda self: len(self._unknown_input_trajectories))
+    num_input_trajectories = property(
+        lambda self: len(self._input_trajectories))
+    previous_discrete_state_symbols = property(lambda self: self._xp)
+    current_discrete_state_symbols = property(lambda self: self._xi)
+    next_discrete_state_symbols = property(lambda self: self._xn)
+    current_known_discrete_specified_symbols = property(lambda self: self._ki)
+    next_known_discrete_specified_symbols = property(lambda self: self._kn)
+    current_unknown_discrete_specified_symbols = property(
+        lambda self: self._ui)
+    next_unknown_discrete_specified_symbols = property(lambda self: self._un)
+    current_discrete_specified_symbols = property(
+        lambda self: self._ki + self._ui)
+    next_discrete_specified_symbols = property(
+        lambda self: self._kn + self._un)
+    parallel = property(lambda self: self._parallel)
+    show_compile_output = property(lambda self: self._show_compile_output)
+    tmp_dir = property(lambda self: self._tmp_dir)
+    node_range = property(lambda self: self._node_range)
+    device = property(lambda self: self._device)
+
+    @integration_method.setter
+    def integration_method(self, method):
+        if method not in _METHODS:
+            raise ValueError('{} is not a valid integration method.'.format(
+                method))
+        self._integration_method = method
+        self._discretize_eom()
+        self._evaluator = None
+
+    # ------------------------------------------------------------------
+    # symbol bookkeeping
+    # ------------------------------------------------------------------
+    @staticmethod
+    def _split_known(everything, known):
+        """Known symbols keep the order the user gave them in, unknown ones
+        are sorted by name (opty/direct_collocation.py:1928-1952)."""
+        everything = set(everything)
+        known = tuple(known)
+        if not everything:
+            if known:
+                raise ValueError('{} are not in the provided equations of '
+                                 'motion.'.format(known))
+            return (), ()
+        return known, tuple(sort_sympy(everything.difference(known)))
+
+    def _classify_parameters(self):
+        # opty/direct_collocation.py:1954-1973
+        symbols = set(self._eom.free_symbols)
+        symbols.discard(self._time_symbol)
+        known, unknown = self._split_known(symbols,
+                                           self._known_parameter_map.keys())
+        self._known_parameters = known
+        self._unknown_parameters = unknown
+        self._parameters = known + unknown
+
+    def _classify_trajectories(self):
+        # opty/direct_collocation.py:1988-2035
+        state_like = set(self._state_symbols) | \
+            set(self._state_derivative_symbols)
+        others = me.find_dynamicsymbols(self._eom).difference(state_like)
+        if any(isinstance(f, sm.Derivative) for f in others):
+            raise ValueError('Too few state variables provided for state '
+                             'time derivatives found in equations of motion.')
+        self._deriv_in_knw_traj = False
+        for f in others:
+            if f.args == (self._time_symbol,):
+                continue
+            if len(f.args) > 1:
+                raise ValueError('{} is a function of more than one '
+                                 'variable.'.format(f))
+            self._deriv_in_knw_traj = True
+        names = [f.name for f in others]
+        if len(set(names)) != len(names):
+            raise ValueError('Repeated input trajectory variable fnames not '
+                             'allowed: {}'.format(names))
+        if self._deriv_in_knw_traj:
+            raise NotImplementedError(
+                'Known trajectories that are implicit functions of time, '
+                'e.g. r(x(t)), are not supported by the cuda backend yet.')
+        known, unknown = self._split_known(others,
+                                           self._known_trajectory_map.keys())
+        self._known_input_trajectories = known
+        self._unknown_input_trajectories = unknown
+        self._input_trajectories = known + unknown
+
+    def _check_known_trajectories(self):
+        # opty/direct_collocation.py:1975-1986
+        N = self._num_collocation_nodes
+        for sym, val in self._known_trajectory_map.items():
+            if _is_callable_value(val):
+                val = val(np.ones(self._num_free))
+            if len(val) != N:
+                raise ValueError('The known parameter {} is not length '
+                                 '{}.'.format(sym, N))
+
+    def _make_discrete_symbols(self):
+        # naming scheme of opty/direct_collocation.py:2070-2118
+        def tagged(funcs, tag):
+            return tuple(sm.Symbol(f.__class__.__name__ + tag, real=True)
+                         for f in funcs)
+        self._xp = tagged(self._state_symbols, 'p')
+        self._xi = tagged(self._state_symbols, 'i')
+        self._xn = tagged(self._state_symbols, 'n')
+        self._ki = tagged(self._known_input_trajectories, 'i')
+        self._kn = tagged(self._known_input_trajectories, 'n')
+        self._ui = tagged(self._unknown_input_trajectories, 'i')
+        self._un = tagged(self._unknown_input_trajectories, 'n')
+
+    def _discretize_eom(self):
+        """Backward Euler: x' -> (xi - xp)/h, x -> xi, u -> ui.  Midpoint:
+        x' -> (xn - xi)/h, x -> (xi + xn)/2, u -> (ui + un)/2
+        (opty/direct_collocation.py:2143-2156)."""
+        logger.info('Discretizing the equations of motion.')
+        h = self._time_interval_symbol
+        x, xd = self._state_symbols, self._state_derivative_symbols
+        u = self._input_trajectories
+        ui = self._ki + self._ui
+        un = self._kn + self._un
+        if self._integration_method == 'backward euler':
+            rates = {d: (c - p) / h for d, c, p in zip(xd, self._xi, self._xp)}
+            values = dict(zip(x + u, self._xi + ui))
+            self._discrete_eom = me.msubs(self._eom, rates, values)
+        else:
+            rates = {d: (nx - c) / h
+                     for d, c, nx in zip(xd, self._xi, self._xn)}
+            mid_x = {f: (c + nx) / 2
+                     for f, c, nx in zip(x, self._xi, self._xn)}
+            mid_u = {f: (c + nx) / 2 for f, c, nx in zip(u, ui, un)}
+            self._discrete_eom = me.msubs(self._eom, rates, mid_x, mid_u)
+
+    # ------------------------------------------------------------------
+    # instance constraints: o scalar expressions, evaluated on the host
+    # (opty/direct_collocation.py:2158-2282)
+    # ------------------------------------------------------------------
+    def _free_index_of(self, func):
+        N = self._num_collocation_nodes
+        arg = func.args[0]
+        if self._variable_duration:
+            if arg == 0:
+                node = 0
+            else:
+                try:
+                    node = int(arg / self._time_interval_symbol)
+                except TypeError as err:
+                    raise TypeError(
+                        'Instance constraint {} is not a correct integer '
+                        'multiple of the time interval.'.format(func)) from err
+            if node not in range(N):
+                raise ValueError(
+                    'Instance constraint {} gives an index of {} which is not '
+                    'between 0 and {}.'.format(func, node, N - 1))
+        else:
+            duration = self._node_time_interval * (N - 1)
+            grid = np.linspace(0.0, duration, num=N)
+            node = int(np.argmin(np.abs(grid - float(arg))))
+        of_time = func.__class__(self._time_symbol)
+        if of_time in self._state_symbols:
+            return node + self._state_symbols.index(of_time) * N
+        if of_time in self._unknown_input_trajectories:
+            return (node + self.num_states * N +
+                    self._unknown_input_trajectories.index(of_time) * N)
+        return None
+
+    def _index_instance_constraints(self):
+        atoms = set()
+        for con in self._instance_constraints:
+            atoms |= con.atoms(sm.Function)
+        self.instance_constraint_function_atoms = atoms
+        self.instance_constraints_free_index_map = {
+            f: self._free_index_of(f) for f in atoms}
+
+    def _instance_lambdify(self, exprs):
+        vec = sm.DeferredVector('FREE')
+        subs = {f: vec[i] for f, i in
+                self.instance_constraints_free_index_map.items()}
+        known = list(self._known_parameter_map.keys())
+        return sm.lambdify([vec] + known, [e.subs(subs) for e in exprs],
+                           modules=[{'ImmutableMatrix': np.array}, 'numpy'])
+
+    def _instance_constraints_func(self):
+        f = self._instance_lambdify(self._instance_constraints)
+        return lambda free: f(free, *self._known_parameter_map.values())
+
+    def _instance_constraints_jacobian_indices(self):
+        # entry order inside one constraint follows ``con.atoms`` exactly as
+        # in the reference (opty/direct_collocation.py:2243-2249)
+        base = self.num_eom * (self._num_collocation_nodes - 1)
+        rows, cols = [], []
+        for i, con in enumerate(self._instance_constraints):
+            for f in con.atoms(sm.Function):
+                rows.append(base + i)
+                cols.append(self.instance_constraints_free_index_map[f])
+        return np.array(rows, dtype=int), np.array(cols, dtype=int)
+
+    def _instance_constraints_jacobian_values_func(self):
+        partials = []
+        for con in self._instance_constraints:
+            partials.extend(con.diff(f) for f in con.atoms(sm.Function))
+        f = self._instance_lambdify(partials)
+        count = len(partials)
+
+        def values(free):
+            out = f(free, *self._known_parameter_map.values())
+            return np.asarray(out, dtype=float).reshape(count)
+        return values
+
+    # ------------------------------------------------------------------
+    # the CUDA evaluator
+    # ------------------------------------------------------------------
+    def _program_inputs(self):
+        """Rows of the device trajectory matrix, the uniform arguments and the
+        differentiation variables.
+
+        Argument order of the reference's generated functions:
+        opty/direct_collocation.py:2345-2364 (constraints) and :2713-2747
+        (Jacobian, which also defines the ``wrt`` = Jacobian column order).
+        """
+        midpoint = self._integration_method == 'midpoint'
+        rows = []
+        if midpoint:
+            rows += list(zip(self._xi, self._xn))
+            rows += list(zip(self._ui, self._un))
+            rows += list(zip(self._ki, self._kn))
+            wrt = self._xi + self._xn + self._ui + self._un
+        else:
+            rows += list(zip(self._xp, self._xi))
+            rows += [(None, s) for s in self._ui]
+            rows += [(None, s) for s in self._ki]
+            wrt = self._xi + self._xp + self._ui
+        wrt += self._unknown_parameters
+        if self._variable_duration:
+            wrt += (self._time_interval_symbol,)
+        uniform = list(self._parameters) + [self._time_interval_symbol]
+        return rows, uniform, list(wrt)
+
+    def _build_evaluator(self):
+        if self._evaluator is None:
+            self._evaluator = _CudaEvaluator(self)
+        return self._evaluator
+
+    def close(self):
+        """Releases the device and pinned host buffers."""
+        if self._evaluator is not None:
+            self._evaluator.close()
+            self._evaluator = None
+
+    def generate_constraint_function(self):
+        """Returns ``f(free) -> ndarray, shape(M*(N-1) + o,)`` ordered
+        ``[eom_1 @ nodes, ..., eom_M @ nodes, c_1..c_o]``
+        (opty/direct_collocation.py:3003-3008, :127-132)."""
+        logger.info('Generating constraint function.')
+        ev = self._build_evaluator()
+        return ev.constraints
+
+    def generate_jacobian_function(self):
+        """Returns ``f(free) -> ndarray, shape(nnz,)``: node-major
+        ``[node][eom][wrt]`` partials followed by the instance-constraint
+        entries (opty/direct_collocation.py:3010-3015, :2681-2688).  The
+        array is a view of a persistent pinned buffer, valid until the next
+        call (the reference returns a view of a persistent buffer too,
+        opty/direct_collocation.py:2814, :2887)."""
+        logger.info('Generating jacobian function.')
+        ev = self._build_evaluator()
+        return ev.jacobian
+
+    def jacobian_indices(self):
+        """COO row and column indices (int64) matching
+        ``generate_jacobian_function``'s values; bit-equal to the reference's
+        Python loop (opty/direct_collocation.py:2450-2690) but generated by a
+        CUDA kernel."""
+        lo, hi = self._node_range
+        method = 1 if self._integration_method == 'midpoint' else 0
+        rows, cols = runtime.jacobian_indices(
+            self._device, self._num_collocation_nodes, lo, hi,
+            self.num_states, self.num_unknown_input_trajectories,
+            self.num_unknown_parameters, int(self._variable_duration),
+            self.num_eom, method)
+        if self._instance_constraints is not None and self._owns_instance():
+            irows, icols = self._instance_constraints_jacobian_indices()
+            rows = np.concatenate((rows, irows.astype(np.int64)))
+            cols = np.concatenate((cols, icols.astype(np.int64)))
+        return rows, cols
+
+    def _owns_instance(self):
+        """Instance constraints are appended only by the collocator that
+        covers the whole node range (shards leave them to the gather step)."""
+        return self._node_range == (0, self._num_collocation_nodes - 1)
+
+
+class _CudaEvaluator(object):
+    """Owns the generated module and the runtime handle of one collocator."""
+
+    def __init__(self, col):
+        self.col = col
+        opts = col._cuda_options
+        rows, uniform, wrt = col._program_inputs()
+        logger.info('Lowering and differentiating the constraint function.')
+        prog = CollocationProgram(list(col.discrete_eom), rows, uniform, wrt,
+                                  use_sympy_cse=opts['use_sympy_cse'])
+        self.program = prog
+        lo, hi = col._node_range
+        nn = hi - lo
+        M, P = prog.M, prog.P
+        K = M * P
+
+        tma_store = bool(opts['tma_store']) and K % 2 == 0
+        tma_load = bool(opts['tma_load']) and prog.R <= 256
+        groups = opts['groups']
+        if groups == 'auto':
+            node_warps = -(-nn // 32)
+            g_par = -(-int(opts['target_warps']) // node_warps)
+            g_cost = int(np.ceil(prog.stats()['varying_cost'] /
+                                 float(opts['max_group_cost'])))
+            groups = max(1, g_par, g_cost)
+        groups = int(min(groups, M, runtime.OPTY_MAX_GROUPS))
+        parts = prog.partition_rows(groups, col_align=2 if tma_store else 1)
+        self.parts = parts
+
+        logger.info('Emitting the CUDA module.')
+        source, meta = codegen.emit_module(
+            prog, parts, col.integration_method,
+            tile_cols=opts['tile_cols'],
+            warps_per_block=opts['warps_per_block'],
+            min_blocks_per_sm=opts['min_blocks_per_sm'],
+            tma_load=tma_load, tma_store=tma_store)
+        self.source = source
+        self.meta = meta
+        flags = build.module_flags(fmad=opts['fmad'],
+                                   maxrregcount=opts['maxrregcount'])
+        logger.info('Compiling the constraint and Jacobian kernels.')
+        cubin, path, hit = build.compile_module(
+            source, flags, cache_dir=col.tmp_dir,
+            show_compile_output=col.show_compile_output)
+        self.cubin_path = path
+        self.cache_hit = hit
+
+        o = col.num_instance_constraints if col._owns_instance() else 0
+        if o:
+            irows, _ = col._instance_constraints_jacobian_indices()
+            nnz_inst = len(irows)
+        else:
+            nnz_inst = 0
+        self.num_inst = o
+        self.nnz_inst = nnz_inst
+
+        cfg = runtime.ColloCfg()
+        cfg.abi_version = runtime.ABI_VERSION
+        cfg.device = col._device
+        cfg.N = col.num_collocation_nodes
+        cfg.node_lo, cfg.node_hi = lo, hi
+        cfg.n = col.num_states
+        cfg.q = col.num_unknown_input_trajectories
+        cfg.k = col.num_known_input_trajectories
+        cfg.r = col.num_unknown_parameters
+        cfg.s = int(col._variable_duration)
+        cfg.pk = col.num_known_parameters
+        cfg.M, cfg.P = M, P
+        cfg.method = 1 if col.integration_method == 'midpoint' else 0
+        cfg.num_inv = meta['num_inv']
+        cfg.num_groups = meta['num_groups']
+        cfg.tile_cols = meta['C']
+        cfg.warps_per_block = meta['warps_per_block']
+        cfg.tma_load = int(meta['tma_load'])
+        cfg.tma_store = int(meta['tma_store'])
+        cfg.out_ring = int(opts['out_ring'])
+        cfg.con_tail = o
+        cfg.jac_tail = nnz_inst
+        for g, gm in enumerate(meta['groups']):
+            cfg.group_col0[g] = gm['col0']
+            cfg.group_ncols[g] = gm['ncols']
+        cfg.h = 0.0 if col._variable_duration else float(
+            col.node_time_interval)
+        self.handle = runtime.ColloHandle(cfg, cubin)
+        self.nn = nn
+        self.con_len = M * nn
+        self.jac_len = nn * K
+
+        self._callable_known = any(
+            _is_callable_value(v) for v in col.known_trajectory_map.values())
+        self._push_known(None)
+
+        if opts['d2h_skip_constants']:
+            self._setup_constant_elision()
+
+    # known values -----------------------------------------------------
+    def _push_known(self, free):
+        col = self.col
+        N = col.num_collocation_nodes
+        traj = None
+        if col.num_known_input_trajectories:
+            traj = np.empty((col.num_known_input_trajectories, N))
+            for i, sym in enumerate(col.known_input_trajectories):
+                val = col.known_trajectory_map[sym]
+                if _is_callable_value(val):
+                    # callables see the free vector on every evaluation
+                    # (opty/direct_collocation.py:2916-2917)
+                    val = val(np.ones(col.num_free) if free is None else free)
+                traj[i] = val
+        params = None
+        if col.num_known_parameters:
+            params = np.array([float(col.known_parameter_map[p])
+                               for p in col.known_parameters])
+        self.handle.set_known(traj, params)
+
+    def _setup_constant_elision(self):
+        """Jacobian columns whose value is a literal for every node (about
+        half of them at the 10-link pendulum) are written to the
+        pinned host buffer once; device->host copies then skip the leading and
+        trailing literal-only column ranges."""
+        kinds = np.array(self.meta['entry_kind'])
+        tape = self.program.tape
+        fill = np.array([tape.val[e] if tape.op[e] == 0 else 0.0
+                         for row in self.program.jac for e in row])
+        nonlit = np.nonzero(kinds != 0)[0]
+        if len(nonlit) == 0:
+            ranges = [(0, 1)]
+        else:
+            # merge runs of non-literal columns separated by short gaps
+            min_gap = 64
+            ranges = []
+            start = prev = int(nonlit[0])
+            for c in nonlit[1:]:
+                c = int(c)
+                if c - prev > min_gap:
+                    ranges.append((start, prev + 1))
+                    start = c
+                prev = c
+            ranges.append((start, prev + 1))
+            if len(ranges) > 8:
+                ranges = [(ranges[0][0], ranges[-1][1])]
+        self.d2h_ranges = ranges
+        self.handle.set_d2h_columns(ranges, fill)
+
+    # callbacks --------------------------------------------------------
+    def _check_free(self, free):
+        free = np.asarray(free, dtype=np.float64)
+        if free.shape != (self.col.num_free,):
+            raise ValueError('free must have shape ({},), got {}.'.format(
+                self.col.num_free, free.shape))
+        return np.ascontiguousarray(free)
+
+    def constraints(self, free):
+        free = self._check_free(free)
+        if self._callable_known:
+            self._push_known(free)
+        buf = self.handle.constraints(free)
+        if self.num_inst:
+            buf[self.con_len:] = self.col.eval_instance_constraints(free)
+        return buf.copy()
+
+    def jacobian(self, free):
+        free = self._check_free(free)
+        if self._callable_known:
+            self._push_known(free)
+        buf = self.handle.jacobian(free)
+        if self.num_inst:
+            buf[self.jac_len:] = \
+                self.col.eval_instance_constraints_jacobian_values(free)
+        return buf
+
+    def close(self):
+        self.handle.close()
+
+
+class Problem(_IpoptBase):
+    """NLP facade with the reference's constructor signature
+    (opty/direct_collocation.py:139-145) and cyipopt callbacks
+    ``objective``, ``gradient``, ``constraints``, ``jacobianstructure``,
+    ``jacobian``, ``intermediate`` (opty/direct_collocation.py:442-567).
+
+    ``free`` is ordered ``[x_1(t_0..t_{N-1}), ..., x_n, u_1, ..., u_q,
+    p_1..p_r, h]`` and the constraints ``[eom_1 @ nodes, ..., eom_M @ nodes,
+    c_1..c_o]`` (opty/direct_collocation.py:116-132).
+    """
+
+    INF = 10e19
+
+    def __init__(self, obj, obj_grad, equations_of_motion, state_symbols,
+                 num_collocation_nodes, node_time_interval,
+                 known_parameter_map={}, known_trajectory_map={},
+                 instance_constraints=None, time_symbol=None, tmp_dir=None,
+                 integration_method='backward euler', parallel=False,
+                 bounds=None, show_compile_output=False, backend='cuda',
+                 eom_bounds=None, device=None, cuda_options=None):
+
+        if not equations_of_motion.has(sm.Derivative):
+            raise ValueError('No time derivatives are present. The equations '
+                             'of motion must be ordinary differential '
+                             'equations (ODEs) or differential algebraic '
+                             'equations (DAEs).')
+
+        self.collocator = ConstraintCollocator(
+            equations_of_motion, state_symbols, num_collocation_nodes,
+            node_time_interval, known_parameter_map, known_trajectory_map,
+            instance_constraints, time_symbol, tmp_dir, integration_method,
+            parallel, show_compile_output=show_compile_output,
+            backend=backend, device=device, cuda_options=cuda_options)
+
+        self._bounds = bounds
+        if eom_bounds is not None:
+            bad = [k for k in eom_bounds
+                   if k not in range(self.collocator.num_eom)]
+            if bad:
+                raise ValueError('Keys {} in eom_bounds do not correspond to '
+                                 'equations of motion.'.format(bad))
+        self._eom_bounds = eom_bounds
+
+        self._obj_num_args = self._count_positional(obj)
+        self._obj_grad_num_args = self._count_positional(obj_grad)
+        if self._obj_num_args not in (1, 2):
+            raise ValueError('The objective function can only have one or '
+                             'two arguments.')
+        if self._obj_grad_num_args not in (1, 2):
+            raise ValueError('The gradient function can only have one or two '
+                             'arguments.')
+        self.obj = obj
+        self.obj_grad = obj_grad
+
+        self.con = self.collocator.generate_constraint_function()
+        logger.info('Constraint function generated.')
+        self.con_jac = self.collocator.generate_jacobian_function()
+        logger.info('Jacobian function generated.')
+        self.con_jac_rows, self.con_jac_cols = \
+            self.collocator.jacobian_indices()
+
+        self.num_free = self.collocator.num_free
+        self.num_constraints = self.collocator.num_constraints
+
+        self._generate_bound_arrays()
+        self._generate_constraint_bound_arrays()
+
+        super(Problem, self).__init__(n=self.num_free, m=self.num_constraints,
+                                      lb=self.lower_bound,
+                                      ub=self.upper_bound,
+                                      cl=self._low_con_bounds,
+                                      cu=self._upp_con_bounds)
+        self.obj_value = []
+
+    @staticmethod
+    def _count_positional(func):
+        code = func.__code__
+        defaults = func.__defaults__
+        return code.co_argcount - (len(defaults) if defaults else 0)
+
+    bounds = property(lambda self: self._bounds)
+    eom_bounds = property(lambda self: self._eom_bounds)
+
+    # -- NLP bounds (host-side set-up, opty/direct_collocation.py:370-440) --
+    def _generate_constraint_bound_arrays(self):
+        low = np.zeros(self.num_constraints)
+        upp = np.zeros(self.num_constraints)
+        if self._eom_bounds is not None:
+            per_eom = self.collocator.num_collocation_nodes - 1
+            for idx, (lo, hi) in self._eom_bounds.items():
+                low[idx * per_eom:(idx + 1) * per_eom] = lo
+                upp[idx * per_eom:(idx + 1) * per_eom] = hi
+        self._low_con_bounds = low
+        self._upp_con_bounds = upp
+
+    def _generate_bound_arrays(self):
+        col = self.collocator
+        N = col.num_collocation_nodes
+        lb = np.full(self.num_free, -self.INF)
+        ub = np.full(self.num_free, self.INF)
+        n, q = col.num_states, col.num_unknown_input_trajectories
+        for var, (lo, hi) in (self._bounds or {}).items():
+            if var in col.state_symbols:
+                sl = slice(col.state_symbols.index(var) * N,
+                           (col.state_symbols.index(var) + 1) * N)
+            elif var in col.unknown_input_trajectories:
+                i = n + col.unknown_input_trajectories.index(var)
+                sl = slice(i * N, (i + 1) * N)
+            elif var in col.unknown_parameters:
+                i = (n + q) * N + col.unknown_parameters.index(var)
+                sl = slice(i, i + 1)
+            elif col._variable_duration and var == col.time_interval_symbol:
+                sl = slice(self.num_free - 1, self.num_free)
+            else:
+                raise ValueError('Bound variable {} not present in free '
+                                 'variables.'.format(var))
+            lb[sl] = lo
+            ub[sl] = hi
+        self.lower_bound = lb
+        self.upper_bound = ub
+
+    # -- callbacks ----------------------------------------------------------
+    def objective(self, free):
+        return self.obj(free) if self._obj_num_args == 1 else \
+            self.obj(self, free)
+
+    def gradient(self, free):
+        return self.obj_grad(free) if self._obj_grad_num_args == 1 else \
+            self.obj_grad(self, free)
+
+    def constraints(self, free):
+        """ndarray, shape(M*(N-1) + o,)"""
+        return self.con(free)
+
+    def jacobianstructure(self):
+        """(rows, cols), each int64 of shape(nnz,)"""
+        return (self.con_jac_rows, self.con_jac_cols)
+
+    def jacobian(self, free):
+        """ndarray, shape(nnz,), aligned with ``jacobianstructure``."""
+        return self.con_jac(free)
+
+    def intermediate(self, *args):
+        self.obj_value.append(args[2])
+
+    def solve(self, free, lagrange=[], zl=[], zu=[], respect_bounds=False):
+        if respect_bounds:
+            self.check_bounds_conflict(free)
+        return super().solve(free, lagrange=lagrange, zl=zl, zu=zu)
+
+    def check_bounds_conflict(self, free):
+        """Raises ValueError if a bound pair is reversed or the guess violates
+        its bounds (opty/direct_collocation.py:317-368)."""
+        reversed_eoms = [k for k, (lo, hi) in (self._eom_bounds or {}).items()
+                         if lo > hi]
+        reversed_vars, outside = [], []
+        for sym, (lo, hi) in (self._bounds or {}).items():
+            if np.any(lo > hi):
+                reversed_vars.append(sym)
+            vals = self.extract_values(free, sym)
+            if np.any(vals < lo) or np.any(vals > hi):
+                outside.append(sym)
+        if outside:
+            raise ValueError('The initial guesses for {} are in conflict '
+                             'with their bounds.'.format(outside))
+        if reversed_eoms or reversed_vars:
+            raise ValueError('The lower bound(s) for {} is (are) greater than '
+                             'the upper bound(s).'.format(
+                                 reversed_eoms + reversed_vars))
+
+    # -- small conveniences used by the callbacks' consumers ----------------
+    def extract_values(self, free, *variables):
+        col = self.collocator
+        N = col.num_collocation_nodes
+        n, q = col.num_states, col.num_unknown_input_trajectories
+        out = []
+        for var in variables:
+            if var in col.state_symbols:
+                i = col.state_symbols.index(var)
+                out.append(free[i * N:(i + 1) * N])
+            elif var in col.unknown_input_trajectories:
+                i = n + col.unknown_input_trajectories.index(var)
+                out.append(free[i * N:(i + 1) * N])
+            elif var in col.unknown_parameters:
+                i = (n + q) * N + col.unknown_parameters.index(var)
+                out.append(free[i:i + 1])
+            elif col._variable_duration and var == col.time_interval_symbol:
+                out.append(free[-1:])
+            else:
+                raise ValueError('{} is not a free variable.'.format(var))
+        return np.concatenate(out)
+
+    def parse_free(self, free):
+        col = self.collocator
+        return parse_free(free, col.num_states,
+                          col.num_unknown_input_trajectories,
+                          col.num_collocation_nodes,
+                          variable_duration=col._variable_duration)

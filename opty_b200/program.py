@@ -1,0 +1,218 @@
+"""Builds the per-node evaluation program of a collocation problem.
+
+Input: the discretised equations of motion (a SymPy column matrix in the
+``...i / ...p / ...n`` discrete symbols, opty/direct_collocation.py:2120-2156)
+together with the layout of the device-side data.  Output: a
+:class:`CollocationProgram` holding one tape with
+
+- the ``M`` constraint residuals of one node
+  (what opty/direct_collocation.py:2375 hands to ``ufuncify_matrix``), and
+- the ``M x P`` partial derivatives of one node
+  (opty/direct_collocation.py:2755, 2800), every entry classified as
+  literal / node-invariant / node-varying,
+
+plus the partition of the EOM rows into *output groups*.  A group is the unit
+of work of one warp in the CUDA kernel (32 lanes = 32 consecutive nodes, all
+executing the same group's straight-line code).
+"""
+
+import hashlib
+
+from . import ir
+from .lowering import lower_matrix
+
+
+class CollocationProgram(object):
+    """
+    Parameters
+    ----------
+    discrete_eom : sequence of SymPy expressions, length M
+    traj_symbols : list of (sym_at_col_i, sym_at_col_i_plus_1)
+        One pair per row of the device trajectory matrix.  For midpoint the
+        pair is (current, next); for backward Euler it is (previous, current).
+        Entries may be None if the symbol does not occur (e.g. inputs under
+        backward Euler have no "previous" symbol).
+    uniform_symbols : list of Symbol
+        Node-invariant arguments in the order of the device ``uni`` array:
+        known parameters, unknown parameters, time interval.
+    wrt : list of Symbol
+        Differentiation variables in reference column order
+        (opty/direct_collocation.py:2719-2721, 2734-2737).
+    """
+
+    def __init__(self, discrete_eom, traj_symbols, uniform_symbols, wrt,
+                 use_sympy_cse=True):
+        self.M = len(discrete_eom)
+        self.P = len(wrt)
+        self.K = self.M * self.P
+        self.R = len(traj_symbols)
+        self.num_uniform = len(uniform_symbols)
+
+        T = ir.Tape()
+        leaf = {}
+        for r, (s0, s1) in enumerate(traj_symbols):
+            if s0 is not None:
+                leaf[s0] = T.vin(2 * r)
+            if s1 is not None:
+                leaf[s1] = T.vin(2 * r + 1)
+        for u, s in enumerate(uniform_symbols):
+            leaf[s] = T.uin(u)
+        self.tape = T
+        self.con = lower_matrix(T, leaf, list(discrete_eom),
+                                use_sympy_cse=use_sympy_cse)
+        wrt_nodes = [leaf[w] for w in wrt]
+        rows = ir.forward_jacobian(T, self.con, wrt_nodes)
+        zero = T.zero
+        # dense M x P table of tape ids, structural zeros point at literal 0
+        self.jac = [[row.get(k, zero) for k in range(self.P)] for row in rows]
+        self._classify()
+
+    # ------------------------------------------------------------------
+    def _classify(self):
+        T = self.tape
+        outs = list(self.con) + [e for row in self.jac for e in row]
+        live = T.reachable(outs)
+        self.live = live
+        varying = T.varying
+        op = T.op
+        # invariant nodes consumed by varying nodes or written as outputs
+        need_inv = set()
+        for i in live:
+            if varying[i]:
+                for o in T.operands(i):
+                    if not varying[o] and op[o] != ir.CONST:
+                        need_inv.add(o)
+        for o in outs:
+            if not varying[o] and op[o] != ir.CONST:
+                need_inv.add(o)
+        self.inv_nodes = sorted(need_inv)
+        self.inv_index = {nid: k for k, nid in enumerate(self.inv_nodes)}
+        self.inv_closure = [i for i in T.reachable(self.inv_nodes)
+                            if op[i] != ir.CONST]
+
+        n_lit = n_inv = n_var = 0
+        for row in self.jac:
+            for e in row:
+                if op[e] == ir.CONST:
+                    n_lit += 1
+                elif varying[e]:
+                    n_var += 1
+                else:
+                    n_inv += 1
+        self.num_literal_entries = n_lit
+        self.num_invariant_entries = n_inv
+        self.num_varying_entries = n_var
+
+    def entry_kind(self):
+        """Returns an ``M*P`` list: 0 literal, 1 node-invariant, 2 varying."""
+        T = self.tape
+        out = []
+        for row in self.jac:
+            for e in row:
+                if T.op[e] == ir.CONST:
+                    out.append(0)
+                elif T.varying[e]:
+                    out.append(2)
+                else:
+                    out.append(1)
+        return out
+
+    # ------------------------------------------------------------------
+    def group_nodes(self, rows):
+        """Node-varying tape ids (topologically sorted) that the outputs of
+        EOM ``rows`` need."""
+        T = self.tape
+        roots = []
+        for j in rows:
+            roots.append(self.con[j])
+            roots.extend(self.jac[j])
+        return [i for i in T.reachable(roots)
+                if T.varying[i] and T.op[i] != ir.VIN]
+
+    def row_costs(self):
+        T = self.tape
+        return [T.cost(self.group_nodes([j])) + 2.0 * self.P
+                for j in range(self.M)]
+
+    def partition_rows(self, num_groups, col_align=2):
+        """Splits the EOM rows into at most ``num_groups`` contiguous ranges
+        of balanced cost.  Each group's first Jacobian column ``r0*P`` is kept
+        a multiple of ``col_align`` (TMA needs 16-byte aligned tile origins).
+
+        Returns a list of ``(r0, r1)``.
+        """
+        M, P = self.M, self.P
+        num_groups = max(1, min(num_groups, M))
+        cuts_ok = [r for r in range(1, M) if (r * P) % col_align == 0]
+        if num_groups == 1 or not cuts_ok:
+            return [(0, M)]
+        # cost of a contiguous range counts shared work once per group, so
+        # evaluate ranges directly (M is small)
+        cost_cache = {}
+
+        def rng_cost(r0, r1):
+            key = (r0, r1)
+            c = cost_cache.get(key)
+            if c is None:
+                c = (self.tape.cost(self.group_nodes(range(r0, r1))) +
+                     2.0 * P * (r1 - r0))
+                cost_cache[key] = c
+            return c
+
+        # minimise the maximum group cost: binary search on the bound with a
+        # greedy feasibility check
+        total = rng_cost(0, M)
+        lo, hi = total / num_groups * 0.5, total
+        best = [(0, M)]
+        for _ in range(24):
+            mid = 0.5 * (lo + hi)
+            parts = []
+            r0 = 0
+            ok = True
+            while r0 < M:
+                r1 = r0 + 1
+                # extend while within the bound and the cut stays legal
+                last_legal = None
+                while r1 <= M:
+                    if r1 == M or r1 in cuts_ok:
+                        if rng_cost(r0, r1) <= mid:
+                            last_legal = r1
+                        else:
+                            break
+                    r1 += 1
+                if last_legal is None:
+                    # a single (legal) block already exceeds the bound
+                    nxt = next((r for r in cuts_ok if r > r0), M)
+                    if rng_cost(r0, nxt) > mid:
+                        ok = False
+                        break
+                    last_legal = nxt
+                parts.append((r0, last_legal))
+                r0 = last_legal
+            if ok and len(parts) <= num_groups:
+                best = parts
+                hi = mid
+            else:
+                lo = mid
+        return best
+
+    def stats(self):
+        T = self.tape
+        var_nodes = [i for i in self.live if T.varying[i] and
+                     T.op[i] != ir.VIN]
+        return {
+            'M': self.M, 'P': self.P, 'R': self.R,
+            'tape_nodes': len(T),
+            'live_nodes': len(self.live),
+            'varying_ops': len(var_nodes),
+            'varying_cost': T.cost(var_nodes),
+            'invariant_table': len(self.inv_nodes),
+            'invariant_ops': len(self.inv_closure),
+            'jac_literal': self.num_literal_entries,
+            'jac_invariant': self.num_invariant_entries,
+            'jac_varying': self.num_varying_entries,
+        }
+
+
+def source_hash(text):
+    return hashlib.sha256(text.encode()).hexdigest()

@@ -1,0 +1,82 @@
+"""TEST INFRASTRUCTURE ONLY: runs an emitted CUDA-C module on the CPU by
+compiling it with g++ against ``tests/host_shim/colloc_kernel.cuh``.
+
+This exists so that the ``-m "not gpu"`` suite can check the emitter's
+arithmetic (lowering, forward-mode differentiation, group partition and tile
+bookkeeping) against the oracle.  Nothing under ``opty_b200/`` imports it.
+"""
+
+import ctypes
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SHIM = os.path.join(_HERE, 'host_shim')
+_BUILD = os.path.join(tempfile.gettempdir(), 'opty_b200_host_harness')
+
+
+def compile_for_host(source):
+    os.makedirs(_BUILD, exist_ok=True)
+    key = hashlib.sha256(source.encode()).hexdigest()[:24]
+    so = os.path.join(_BUILD, 'mod_{}.so'.format(key))
+    if not os.path.exists(so):
+        src = os.path.join(_BUILD, 'mod_{}.cpp'.format(key))
+        with open(src, 'w') as f:
+            f.write(source)
+        # -ffp-contract=off: no FMA contraction, like nvcc --fmad=false
+        cmd = ['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-w',
+               '-I', SHIM, '-o', so, src]
+        subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return ctypes.CDLL(so)
+
+
+def host_evaluate(collocator, free, known_traj=None):
+    """Evaluates constraints and Jacobian of ``collocator`` (an
+    ``opty_b200.ConstraintCollocator``) at ``free`` with the emitted code
+    compiled for the host.  Returns ``(con, jac)`` in the reference layouts
+    (eom-major residuals, node-major partials), EOM part only."""
+    from opty_b200 import codegen
+    from opty_b200.program import CollocationProgram
+    rows, uniform, wrt = collocator._program_inputs()
+    opts = collocator._cuda_options
+    prog = CollocationProgram(list(collocator.discrete_eom), rows, uniform,
+                              wrt, use_sympy_cse=opts['use_sympy_cse'])
+    groups = opts['groups']
+    if groups == 'auto':
+        groups = 3
+    parts = prog.partition_rows(int(groups), col_align=2)
+    source, meta = codegen.emit_module(prog, parts,
+                                       collocator.integration_method,
+                                       tile_cols=opts['tile_cols'])
+    lib = compile_for_host(source)
+    N = collocator.num_collocation_nodes
+    n = collocator.num_states
+    q = collocator.num_unknown_input_trajectories
+    k = collocator.num_known_input_trajectories
+    r = collocator.num_unknown_parameters
+    free = np.ascontiguousarray(free, dtype=float)
+    traj = np.zeros((n + q + k, N))
+    traj[:n + q] = free[:(n + q) * N].reshape(n + q, N)
+    for i, sym in enumerate(collocator.known_input_trajectories):
+        val = collocator.known_trajectory_map[sym]
+        traj[n + q + i] = val(free) if callable(val) else val
+    uni = [float(collocator.known_parameter_map[p])
+           for p in collocator.known_parameters]
+    uni += list(free[(n + q) * N:(n + q) * N + r])
+    if collocator._variable_duration:
+        uni.append(free[-1])
+    else:
+        uni.append(float(collocator.node_time_interval))
+    uni = np.array(uni, dtype=float)
+    nn = N - 1
+    con = np.empty(prog.M * nn)
+    jac = np.empty(nn * prog.K)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.host_eval.argtypes = [dp, dp, ctypes.c_longlong, ctypes.c_int, dp, dp]
+    lib.host_eval(uni.ctypes.data_as(dp), traj.ctypes.data_as(dp), N, nn,
+                  con.ctypes.data_as(dp), jac.ctypes.data_as(dp))
+    return con, jac
