@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the collocation constraint + Jacobian hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Metric (BASELINE.json): constraint+Jacobian evals/sec on the 10-link pendulum
+at 10 000 midpoint nodes (``configs[1]``); one *eval* = one
+``Problem.constraints(free)`` + one ``Problem.jacobian(free)`` at the same
+``free``.  One *step* = one eval.
+
+Own arm
+    ``value``   K device-resident evals (free vector already in HBM, results
+                left in HBM), timed with CUDA events on the launching stream,
+                max over ranks.
+    ``e2e``     K evals through the public API with HOST arrays: H2D of the
+                free vector, kernels, D2H of residuals and Jacobian inside the
+                timed region.
+    ``roofline``  algorithmic bytes of one fused launch / average launch
+                duration, against the measured HBM peak.
+    ``cpu_baseline``  the CPU oracle (a port of the reference's generated
+                C + loop, bit-identical to it on this workload) on the host
+                cores, on a bounded number of evals.
+
+Reference arm (``--impl reference``): the same workload evaluated by the CPU
+oracle with all host threads (OpenMP), rank 0 only.
+
+With N > 1 the constraint nodes are sharded: the problem has ``N * 9999``
+constraint nodes and rank g evaluates nodes ``[g*9999, (g+1)*9999)`` -- weak
+scaling, no data-path collective.  ``value`` is reported in
+10k-node-problem evals per second summed over the ranks.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'constraint+Jacobian evals/sec, 10-link pendulum @ 10k nodes'
+UNIT = 'evals/s'
+LINKS = 10
+NODES_PER_RANK = 10000          # collocation nodes of BASELINE configs[1]
+WORKLOAD = ('configs[1]: 10-link inverted pendulum on cart, 10 000 midpoint '
+            'nodes, n=M=22, q=1, all constants known, seeded N(0,1) free '
+            'vector (SURVEY.md §8d)')
+OUT_RING = 4                    # 4 x 83 MB output sets > 126 MB L2
+
+
+def _peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured'
+    except (OSError, ValueError, KeyError):
+        return 6650.0, 'fallback'
+
+
+class ClockSampler(object):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed
+    regions run (B200_PROFILING.md)."""
+
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,'
+             'clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(device), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax = [], []
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {'sm_mhz': float(np.median(sm)),
+                'sm_max_mhz': float(np.max(smax)),
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def build_workload(world):
+    import workloads
+    n_total = (NODES_PER_RANK - 1) * world + 1
+    return workloads.n_link_pendulum(LINKS, n_total)
+
+
+def algorithmic_bytes(n, q, k, r, s, M, P, N_cols, nodes):
+    """Bytes of one fused constraint+Jacobian launch: the
+    trajectory columns and free scalars read once, every residual and every
+    Jacobian entry (structural zeros included) written once."""
+    return 8 * ((n + q + k) * N_cols + r + s + M * nodes + nodes * M * P)
+
+
+# ---------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """The reference's CPU path (oracle port, all host threads)."""
+    if rank != 0:
+        return
+    from oracle.opty_oracle import OracleCollocator
+    w = build_workload(1)
+    threads = os.cpu_count() or 1
+    os.environ.setdefault('OMP_NUM_THREADS', str(threads))
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs(),
+                           parallel=True)
+    free = w.free(orc.num_free)
+    frees = [free, free + 1e-3]
+    for i in range(max(args.warmup, 1)):
+        orc.constraints(frees[i % 2])
+        orc.jacobian(frees[i % 2])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        orc.constraints(frees[i % 2])
+        orc.jacobian(frees[i % 2])
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD,
+                   'note': 'CPU only: reference algorithm (oracle port of '
+                           'the generated C + node loop, gcc -O2 -fopenmp), '
+                           'one full 10k-node eval per step'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads,
+                         'kind': 'port',
+                         'sample': '{} full evals (constraints + jacobian) '
+                                   'of the 10k-node workload'.format(
+                                       args.steps)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(budget_s=12.0):
+    """Oracle timed on the host cores: serial and OpenMP."""
+    from oracle.opty_oracle import OracleCollocator
+    w = build_workload(1)
+    out = {}
+    threads = os.cpu_count() or 1
+    for label, par in (('serial', False), ('parallel', True)):
+        orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs(),
+                               parallel=par)
+        free = w.free(orc.num_free)
+        orc.constraints(free)
+        orc.jacobian(free)
+        count = 0
+        t0 = time.perf_counter()
+        while True:
+            orc.constraints(free)
+            orc.jacobian(free)
+            count += 1
+            dt = time.perf_counter() - t0
+            if dt > budget_s / 2 or count >= 200:
+                break
+        out[label] = (count / dt, count)
+    return {'value': out['parallel'][0], 'unit': UNIT, 'cores': threads,
+            'kind': 'port',
+            'sample': '{} full evals of the 10k-node workload with OpenMP on '
+                      '{} threads (serial, 1 core: {:.2f} evals/s over {} '
+                      'evals)'.format(out['parallel'][1], threads,
+                                      out['serial'][0], out['serial'][1]),
+            'serial_value': out['serial'][0]}
+
+
+def run_own_arm(args, rank, world, local_rank):
+    import torch
+    from opty_b200 import ConstraintCollocator
+
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback).')
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(
+            'cuda', local_rank))
+
+    w = build_workload(world)
+    nn = NODES_PER_RANK - 1
+    node_range = (rank * nn, (rank + 1) * nn)
+    col = ConstraintCollocator(
+        *w.collocator_args(), **w.collocator_kwargs(), device=local_rank,
+        node_range=node_range, cuda_options={'out_ring': OUT_RING})
+    con_f = col.generate_constraint_function()
+    jac_f = col.generate_jacobian_function()
+    ev = col._evaluator
+    h = ev.handle
+    free = w.free(col.num_free)
+    frees = [free, free + 1e-3]
+    prog = ev.program
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---- device-resident evals ------------------------------------------
+    h.upload_free(free)
+    h.time_device_evals(max(args.warmup, 3))
+    launches0 = h.launch_count()
+    barrier()
+    ms = h.time_device_evals(args.steps)
+    barrier()
+    launches = h.launch_count() - launches0
+    per_launch_ms = []
+    for _ in range(min(args.steps, 50)):
+        h.eval_device(sync=True)
+        per_launch_ms.append(h.last_kernel_ms())
+    if dist is not None:
+        t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API ----------------------------------
+    for i in range(max(args.warmup, 3)):
+        con_f(frees[i % 2])
+        jac_f(frees[i % 2])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        con = con_f(frees[i % 2])
+        jac = jac_f(frees[i % 2])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * args.steps / e2e_s
+    h2d = 8 * ((col.num_states + col.num_unknown_input_trajectories) *
+               (nn + 1) + col.num_unknown_parameters +
+               int(col._variable_duration))
+    ranges = getattr(ev, 'd2h_ranges', [(0, prog.K)])
+    d2h = 8 * (prog.M * nn + nn * sum(e - b for b, e in ranges))
+    assert con.shape == (prog.M * nn,) and jac.shape == (nn * prog.K,)
+
+    clocks = sampler.stop() if sampler is not None else None
+
+    if rank == 0:
+        peak, peak_kind = _peaks()
+        bytes_launch = algorithmic_bytes(
+            col.num_states, col.num_unknown_input_trajectories,
+            col.num_known_input_trajectories, col.num_unknown_parameters,
+            int(col._variable_duration), prog.M, prog.P, nn + 1, nn)
+        launch_ms = ms / args.steps
+        achieved = bytes_launch / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get('dram_bytes_per_launch')
+            except (OSError, ValueError):
+                traffic = None
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': launch_ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {
+                'workload': WORKLOAD,
+                'nodes_per_gpu': nn, 'parallelism': 'node-shard x{}'.format(
+                    world),
+                'groups': ev.meta['num_groups'],
+                'tile_cols': ev.meta['C'],
+                'tma_load': ev.meta['tma_load'],
+                'tma_store': ev.meta['tma_store'],
+                'l2': 'rotating {} device output sets ({:.0f} MB) > 126 MB '
+                      'L2'.format(OUT_RING, OUT_RING * 8e-6 * (
+                          prog.M * nn + nn * prog.K)),
+                'e2e_d2h': 'literal-only Jacobian column ranges are written '
+                           'to the pinned buffer once and not re-copied; '
+                           'copied columns: {}'.format(ranges),
+            },
+            'roofline': {
+                'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                'peak_kind': peak_kind,
+                'algorithmic_bytes_per_launch': bytes_launch,
+                'kernel': 'opty_colloc_eval',
+                'launch_ms_avg': launch_ms,
+                'launch_ms_median_isolated': float(np.median(per_launch_ms)),
+            },
+            'e2e': {'value': e2e_value, 'unit': UNIT,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': 1e3 * e2e_s / args.steps},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    col.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+    else:
+        run_own_arm(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -137,6 +137,11 @@ int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t*
 /* CUDA-event duration (ms) of the kernels of the last evaluation. */
 int opty_colloc_last_kernel_ms(opty_colloc_t* h, float* ms);
 
+/* Measurement aid: launches `steps` device-resident evaluations back to back
+ * on the handle's stream, bracketed by two CUDA events recorded on that same
+ * stream, waits, and returns the elapsed device time of the batch in ms. */
+int opty_colloc_time_device_evals(opty_colloc_t* h, int steps, float* total_ms);
+
 /* Number of kernel launches issued by this handle so far. */
 int opty_colloc_launch_count(opty_colloc_t* h, int64_t* count);
 

@@ -551,6 +551,26 @@ int opty_colloc_last_kernel_ms(opty_colloc_t* h, float* ms) {
   return OPTY_OK;
 }
 
+int opty_colloc_time_device_evals(opty_colloc_t* h, int steps, float* total_ms) {
+  if (!h || !total_ms || steps < 1) return fail(OPTY_ERR_ARG, "invalid argument");
+  RT_CHECK(cudaSetDevice(h->cfg.device));
+  cudaEvent_t a, b;
+  RT_CHECK(cudaEventCreate(&a));
+  RT_CHECK(cudaEventCreate(&b));
+  RT_CHECK(cudaStreamSynchronize(h->stream));
+  RT_CHECK(cudaEventRecord(a, h->stream));
+  int rc = OPTY_OK;
+  for (int i = 0; i < steps && rc == OPTY_OK; ++i) rc = launch_eval(h);
+  cudaEventRecord(b, h->stream);
+  cudaError_t e = cudaEventSynchronize(b);
+  if (rc == OPTY_OK && e == cudaSuccess) e = cudaEventElapsedTime(total_ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(OPTY_ERR_CUDA, std::string("timing failed: ") + cudaGetErrorString(e));
+  return OPTY_OK;
+}
+
 int opty_colloc_launch_count(opty_colloc_t* h, int64_t* count) {
   if (!h || !count) return fail(OPTY_ERR_ARG, "null argument");
   *count = h->launches;

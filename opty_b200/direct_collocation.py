@@ -464,6 +464,11 @@ class ConstraintCollocator(object):
         uniform = list(self._parameters) + [self._time_interval_symbol]
         return rows, uniform, list(wrt)
 
+    def prepare_module(self):
+        """Lowers, emits and compiles this problem's CUDA module without
+        touching a GPU; returns the ``_PreparedModule``."""
+        return _PreparedModule(self)
+
     def _build_evaluator(self):
         if self._evaluator is None:
             self._evaluator = _CudaEvaluator(self)
@@ -518,11 +523,12 @@ class ConstraintCollocator(object):
         return self._node_range == (0, self._num_collocation_nodes - 1)
 
 
-class _CudaEvaluator(object):
-    """Owns the generated module and the runtime handle of one collocator."""
+class _PreparedModule(object):
+    """Tape program, emitted CUDA-C and compiled cubin of one collocator.
+    Building it needs nvcc but no GPU (``__graft_entry__.build`` uses this to
+    fill the compiled-module cache ahead of time)."""
 
     def __init__(self, col):
-        self.col = col
         opts = col._cuda_options
         rows, uniform, wrt = col._program_inputs()
         logger.info('Lowering and differentiating the constraint function.')
@@ -531,8 +537,8 @@ class _CudaEvaluator(object):
         self.program = prog
         lo, hi = col._node_range
         nn = hi - lo
-        M, P = prog.M, prog.P
-        K = M * P
+        M = prog.M
+        K = M * prog.P
 
         tma_store = bool(opts['tma_store']) and K % 2 == 0
         tma_load = bool(opts['tma_load']) and prog.R <= 256
@@ -544,26 +550,42 @@ class _CudaEvaluator(object):
                                  float(opts['max_group_cost'])))
             groups = max(1, g_par, g_cost)
         groups = int(min(groups, M, runtime.OPTY_MAX_GROUPS))
-        parts = prog.partition_rows(groups, col_align=2 if tma_store else 1)
-        self.parts = parts
+        self.parts = prog.partition_rows(groups,
+                                         col_align=2 if tma_store else 1)
 
         logger.info('Emitting the CUDA module.')
-        source, meta = codegen.emit_module(
-            prog, parts, col.integration_method,
+        self.source, self.meta = codegen.emit_module(
+            prog, self.parts, col.integration_method,
             tile_cols=opts['tile_cols'],
             warps_per_block=opts['warps_per_block'],
             min_blocks_per_sm=opts['min_blocks_per_sm'],
             tma_load=tma_load, tma_store=tma_store)
-        self.source = source
-        self.meta = meta
         flags = build.module_flags(fmad=opts['fmad'],
                                    maxrregcount=opts['maxrregcount'])
         logger.info('Compiling the constraint and Jacobian kernels.')
-        cubin, path, hit = build.compile_module(
-            source, flags, cache_dir=col.tmp_dir,
+        self.cubin, self.cubin_path, self.cache_hit = build.compile_module(
+            self.source, flags, cache_dir=col.tmp_dir,
             show_compile_output=col.show_compile_output)
-        self.cubin_path = path
-        self.cache_hit = hit
+
+
+class _CudaEvaluator(object):
+    """Owns the generated module and the runtime handle of one collocator."""
+
+    def __init__(self, col):
+        self.col = col
+        opts = col._cuda_options
+        prepared = _PreparedModule(col)
+        prog = self.program = prepared.program
+        self.parts = prepared.parts
+        self.source = prepared.source
+        meta = self.meta = prepared.meta
+        cubin = prepared.cubin
+        self.cubin_path = prepared.cubin_path
+        self.cache_hit = prepared.cache_hit
+        lo, hi = col._node_range
+        nn = hi - lo
+        M, P = prog.M, prog.P
+        K = M * P
 
         o = col.num_instance_constraints if col._owns_instance() else 0
         if o:

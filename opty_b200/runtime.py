@@ -21,7 +21,8 @@ EXPORTS = (
     'opty_colloc_eval_device', 'opty_colloc_constraints',
     'opty_colloc_jacobian', 'opty_colloc_host_buffers',
     'opty_colloc_device_buffers', 'opty_colloc_set_d2h_columns',
-    'opty_colloc_last_kernel_ms', 'opty_colloc_launch_count',
+    'opty_colloc_last_kernel_ms', 'opty_colloc_time_device_evals',
+    'opty_colloc_launch_count',
     'opty_colloc_jacobian_indices', 'opty_colloc_last_error',
 )
 
@@ -96,6 +97,8 @@ def load_library(path=None):
                                                 c_vp, c_vp]
     lib.opty_colloc_last_kernel_ms.argtypes = [c_vp,
                                                ctypes.POINTER(ctypes.c_float)]
+    lib.opty_colloc_time_device_evals.argtypes = [
+        c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
     lib.opty_colloc_launch_count.argtypes = [c_vp,
                                              ctypes.POINTER(ctypes.c_int64)]
     lib.opty_colloc_jacobian_indices.argtypes = [ctypes.c_int] * 10 + [c_vp,
@@ -240,6 +243,14 @@ class ColloHandle(object):
         ms = ctypes.c_float()
         _check(self.lib, self.lib.opty_colloc_last_kernel_ms(
             self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def time_device_evals(self, steps):
+        """Device time (ms, CUDA events on the launching stream) of ``steps``
+        back-to-back device-resident evaluations."""
+        ms = ctypes.c_float()
+        _check(self.lib, self.lib.opty_colloc_time_device_evals(
+            self._h, int(steps), ctypes.byref(ms)))
         return ms.value
 
     def launch_count(self):

@@ -1,0 +1,365 @@
+"""Parity tests proper: the CUDA path -- called through the facade, which
+calls through the C-ABI of include/opty_b200.h -- against the CPU oracle on
+the same seeded inputs, against the golden vectors produced by the reference
+itself, against the reference's hand-computed known answers, and through
+size-independent properties at the full BASELINE config 2 size.
+
+Bar: ``jacobianstructure`` bit-exact (int64), values within 1e-10 relative
+(criterion spelled out in conftest.assert_values_close)."""
+
+import hashlib
+
+import numpy as np
+import pytest
+
+import cases
+import workloads
+from conftest import assert_values_close, load_golden
+from opty_b200 import ConstraintCollocator, Problem, runtime
+from oracle.opty_oracle import OracleCollocator
+
+pytestmark = pytest.mark.gpu
+
+
+def _digest(arr):
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+
+
+def _collocator(w, **kw):
+    return ConstraintCollocator(*w.collocator_args(),
+                                **w.collocator_kwargs(), **kw)
+
+
+def _eom_sizes(col):
+    nn = col.num_collocation_nodes - 1
+    M = col.num_eom
+    return nn, M
+
+
+# ---------------------------------------------------------------------------
+# known answers (hand-computed in the reference's tests)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('case', cases.all_cases(), ids=lambda c: c.name)
+def test_known_answers(case):
+    col = ConstraintCollocator(*case.collocator_args(),
+                               **case.collocator_kwargs())
+    con = col.generate_constraint_function()(case.free)
+    jac = np.array(col.generate_jacobian_function()(case.free))
+    rows, cols = col.jacobian_indices()
+    assert con.shape == case.expected_con.shape
+    assert jac.shape == case.expected_jac.shape
+    np.testing.assert_allclose(con, case.expected_con, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(jac, case.expected_jac, rtol=1e-12, atol=1e-9)
+    assert rows.dtype == np.int64 and cols.dtype == np.int64
+    assert len(rows) == len(cols) == len(jac)
+    if case.expected_rows is not None:
+        assert np.array_equal(rows, case.expected_rows)
+        assert np.array_equal(cols, case.expected_cols)
+    col.close()
+
+
+# ---------------------------------------------------------------------------
+# golden vectors produced by the reference (tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------
+GOLDEN = [
+    ('cfg1_pendulum_swing_up_N51', lambda: workloads.pendulum_swing_up(51)),
+    ('cfg3_vyasarayani2011_N5000', lambda: workloads.vyasarayani2011(5000)),
+    ('cfg3_vyasarayani2011_N101_odd',
+     lambda: workloads.vyasarayani2011(101, seed=5)),
+    ('cfg4_standin_pendulum4_torques_N200',
+     lambda: workloads.n_link_pendulum_torques(4, 200)),
+    ('cfg2_small_pendulum10_N40',
+     lambda: workloads.n_link_pendulum(10, 40, seed=7)),
+]
+
+
+@pytest.mark.parametrize('name,make', GOLDEN, ids=[g[0] for g in GOLDEN])
+def test_matches_reference_golden(name, make):
+    gold = load_golden(name)
+    w = make()
+    col = _collocator(w)
+    free = w.free(col.num_free)
+    assert np.array_equal(free, gold['free'])
+    con = col.generate_constraint_function()(free)
+    jac = np.array(col.generate_jacobian_function()(free))
+    rows, cols = col.jacobian_indices()
+    # jacobianstructure: bit-exact
+    assert np.array_equal(rows, gold['rows'])
+    assert np.array_equal(cols, gold['cols'])
+    nn, M = _eom_sizes(col)
+    P = col._evaluator.program.P
+    assert con.shape == gold['con'].shape and jac.shape == gold['jac'].shape
+    assert_values_close(con[:M * nn], gold['con'][:M * nn])
+    assert_values_close(jac[:nn * M * P], gold['jac'][:nn * M * P], row_len=P)
+    # instance-constraint parts (host lambdify in both implementations)
+    np.testing.assert_allclose(con[M * nn:], gold['con'][M * nn:],
+                               rtol=1e-13, atol=0)
+    np.testing.assert_allclose(jac[nn * M * P:], gold['jac'][nn * M * P:],
+                               rtol=1e-13, atol=0)
+    col.close()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE config 2 at full size
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def config2():
+    w = workloads.n_link_pendulum(10, 10000)
+    col = _collocator(w)
+    free = w.free(col.num_free)
+    con_f = col.generate_constraint_function()
+    jac_f = col.generate_jacobian_function()
+    con = con_f(free)
+    jac = np.array(jac_f(free))
+    yield w, col, free, con, jac
+    col.close()
+
+
+def test_config2_against_reference_sample_and_structure_digest(config2):
+    w, col, free, con, jac = config2
+    gold = load_golden('cfg2_pendulum10_N10000')
+    assert _digest(free) == str(gold['free_sha256'])
+    nn, M = _eom_sizes(col)
+    K = M * col._evaluator.program.P
+    assert len(jac) == int(gold['nnz']) == 10118988
+    nodes = gold['nodes']
+    assert_values_close(con.reshape(M, nn)[:, nodes], gold['con'])
+    assert_values_close(jac.reshape(nn, K)[nodes].ravel(),
+                        gold['jac'].ravel(), row_len=K // M)
+    rows, cols = col.jacobian_indices()
+    assert rows.dtype == np.int64 and cols.dtype == np.int64
+    # all 10 118 988 COO entries bit-equal to the reference's
+    assert _digest(rows) == str(gold['rows_sha256'])
+    assert _digest(cols) == str(gold['cols_sha256'])
+
+
+def test_config2_against_oracle_full_size(config2):
+    w, col, free, con, jac = config2
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    ocon = orc.constraints(free)
+    ojac = orc.jacobian(free)
+    P = col._evaluator.program.P
+    assert_values_close(con, ocon)
+    assert_values_close(jac, ojac, row_len=P)
+    # and plainly: the worst element-wise relative deviation stays below 1e-10
+    big = np.abs(ojac) > 1e-6
+    assert np.max(np.abs(jac[big] - ojac[big]) / np.abs(ojac[big])) < 1e-10
+    big = np.abs(ocon) > 1e-6
+    assert np.max(np.abs(con[big] - ocon[big]) / np.abs(ocon[big])) < 1e-10
+
+
+def test_config2_properties(config2):
+    w, col, free, con, jac = config2
+    nn, M = _eom_sizes(col)
+    P = col._evaluator.program.P
+    K = M * P
+    N = col.num_collocation_nodes
+    con_f = col.generate_constraint_function()
+    jac_f = col.generate_jacobian_function()
+
+    # (1) deterministic: a second evaluation gives identical bits
+    f2 = free.copy()
+    f2[0] += 1.0
+    con_f(f2)                      # move away ...
+    assert np.array_equal(con_f(free), con)      # ... and back
+    assert np.array_equal(np.array(jac_f(free)), jac)
+
+    # (2) locality: node i only depends on trajectory columns i and i+1.
+    # Perturbing column c changes exactly the node blocks c-1 and c.
+    c = 4321
+    f3 = free.copy()
+    f3[c::N][:col.num_states] += 0.25
+    j3 = np.array(jac_f(f3)).reshape(nn, K)
+    c3 = con_f(f3).reshape(M, nn)
+    changed = np.nonzero(np.any(j3 != jac.reshape(nn, K), axis=1))[0]
+    assert set(changed) <= {c - 1, c} and len(changed) > 0
+    changed = np.nonzero(np.any(c3 != con.reshape(M, nn), axis=0))[0]
+    assert set(changed) == {c - 1, c}
+
+    # (3) translation: shifting the trajectories by one node shifts the node
+    # blocks by one (the kernel has no dependence on the absolute node index)
+    rows_total = col.num_states + col.num_unknown_input_trajectories
+    traj = free[:rows_total * N].reshape(rows_total, N)
+    f4 = free.copy()
+    f4[:rows_total * N] = np.roll(traj, -1, axis=1).ravel()
+    j4 = np.array(jac_f(f4)).reshape(nn, K)
+    c4 = con_f(f4).reshape(M, nn)
+    assert np.array_equal(j4[:nn - 1], jac.reshape(nn, K)[1:])
+    assert np.array_equal(c4[:, :nn - 1], con.reshape(M, nn)[:, 1:])
+
+    # (4) the Jacobian is the derivative of the residuals: directional
+    # finite difference at full size (coo_matvec with the bit-exact structure)
+    rows, cols = col.jacobian_indices()
+    rng = np.random.default_rng(5)
+    d = rng.standard_normal(free.size)
+    eps = 1e-6
+    fd = (con_f(free + eps * d) - con_f(free - eps * d)) / (2 * eps)
+    jv = np.bincount(rows, weights=jac * d[cols], minlength=len(con))
+    assert np.max(np.abs(fd - jv)) <= 1e-5 * np.max(np.abs(jv))
+
+
+def test_config2_kernel_variants_agree_bitwise(config2):
+    """Group count, tile width, TMA vs warp-per-node stores and block size
+    change the schedule, not the arithmetic: results must be bit-identical."""
+    w, col, free, con, jac = config2
+    variants = [
+        {'groups': 1, 'tile_cols': 46},
+        {'groups': 11, 'tile_cols': 14, 'warps_per_block': 4},
+        {'tma_store': False, 'tma_load': False, 'groups': 5},
+        {'d2h_skip_constants': False, 'groups': 3, 'out_ring': 3},
+    ]
+    for opts in variants:
+        other = _collocator(w, cuda_options=opts)
+        c2 = other.generate_constraint_function()(free)
+        j2 = np.array(other.generate_jacobian_function()(free))
+        assert np.array_equal(c2, con), opts
+        assert np.array_equal(j2, jac), opts
+        other.close()
+
+
+def test_config2_fused_multiply_add_build_stays_in_tolerance(config2):
+    w, col, free, con, jac = config2
+    other = _collocator(w, cuda_options={'fmad': True})
+    P = col._evaluator.program.P
+    assert_values_close(other.generate_constraint_function()(free), con)
+    assert_values_close(np.array(other.generate_jacobian_function()(free)),
+                        jac, row_len=P)
+    other.close()
+
+
+def test_node_range_shards_reproduce_the_whole(config2):
+    """Sharding the constraint nodes (multi-GPU decomposition, here on one
+    device) reproduces the unsharded result bit for bit."""
+    w, col, free, con, jac = config2
+    nn, M = _eom_sizes(col)
+    K = M * col._evaluator.program.P
+    rows, cols = col.jacobian_indices()
+    bounds = [0, 1, 2500, 7001, nn]
+    for lo, hi in zip(bounds, bounds[1:]):
+        part = _collocator(w, node_range=(lo, hi))
+        c = part.generate_constraint_function()(free)
+        j = np.array(part.generate_jacobian_function()(free))
+        r, cc = part.jacobian_indices()
+        assert np.array_equal(c.reshape(M, hi - lo),
+                              con.reshape(M, nn)[:, lo:hi])
+        assert np.array_equal(j, jac[lo * K:hi * K])
+        assert np.array_equal(r, rows[lo * K:hi * K])
+        assert np.array_equal(cc, cols[lo * K:hi * K])
+        part.close()
+
+
+# ---------------------------------------------------------------------------
+# stand-in for BASELINE config 4 at a larger size, against the oracle
+# ---------------------------------------------------------------------------
+def test_config4_standin_against_oracle():
+    w = workloads.n_link_pendulum_torques(4, 2000)
+    col = _collocator(w)
+    free = w.free(col.num_free)
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    con = col.generate_constraint_function()(free)
+    jac = np.array(col.generate_jacobian_function()(free))
+    ocon, ojac = orc.constraints(free), orc.jacobian(free)
+    nn, M = _eom_sizes(col)
+    P = col._evaluator.program.P
+    assert_values_close(con[:M * nn], ocon[:M * nn])
+    assert_values_close(jac[:nn * M * P], ojac[:nn * M * P], row_len=P)
+    np.testing.assert_allclose(con[M * nn:], ocon[M * nn:], rtol=1e-13)
+    np.testing.assert_allclose(jac[nn * M * P:], ojac[nn * M * P:],
+                               rtol=1e-13)
+    rows, cols = col.jacobian_indices()
+    orows, ocols = orc.jacobian_indices()
+    assert np.array_equal(rows, orows) and np.array_equal(cols, ocols)
+    # a new value of the free time interval / parameters is picked up
+    f2 = free.copy()
+    f2[-1] *= 1.5
+    f2[-2] += 0.1
+    assert_values_close(col.generate_constraint_function()(f2)[:M * nn],
+                        orc.constraints(f2)[:M * nn])
+    assert_values_close(
+        np.array(col.generate_jacobian_function()(f2))[:nn * M * P],
+        orc.jacobian(f2)[:nn * M * P], row_len=P)
+    col.close()
+
+
+# ---------------------------------------------------------------------------
+# boundary behaviour
+# ---------------------------------------------------------------------------
+def test_problem_callback_surface():
+    """Shapes, dtypes and ownership of the cyipopt callbacks
+    (opty/direct_collocation.py:498-562)."""
+    w = workloads.pendulum_swing_up(51)
+    prob = Problem(lambda fr: float(np.sum(fr**2)), lambda fr: 2.0 * fr,
+                   *w.collocator_args(), **w.collocator_kwargs(),
+                   bounds={w.states[0]: (-10.0, 10.0)},
+                   eom_bounds={0: (-20.0, 20.0)})
+    free = w.free(prob.num_free)
+    assert prob.num_free == 153 and prob.num_constraints == 104
+    g = prob.constraints(free)
+    assert g.shape == (104,) and g.dtype == np.float64
+    rows, cols = prob.jacobianstructure()
+    vals = prob.jacobian(free)
+    assert vals.shape == rows.shape == cols.shape == (504,)
+    assert rows.dtype == np.int64
+    assert prob.objective(free) == float(np.sum(free**2))
+    assert prob.gradient(free).shape == (153,)
+    assert np.all(prob.lower_bound[:51] == -10.0)
+    assert np.all(prob._low_con_bounds[:50] == -20.0)
+    prob.intermediate(0, 0, 1.5)
+    assert prob.obj_value == [1.5]
+    # constraints() returns a fresh array; jacobian() a persistent buffer that
+    # the next call overwrites (opty/direct_collocation.py:2814, 2887)
+    g2 = prob.constraints(free + 1.0)
+    assert not np.shares_memory(g, g2) and not np.array_equal(g, g2)
+    v1 = np.array(vals)
+    v2 = prob.jacobian(free + 1.0)
+    assert np.shares_memory(vals, v2)
+    assert not np.array_equal(v1, np.array(v2))
+    with pytest.raises(ValueError):
+        prob.constraints(free[:-1])
+    with pytest.raises(ValueError):
+        prob.jacobian(np.zeros((153, 1)))
+    prob.collocator.close()
+
+
+def test_callable_known_trajectory_sees_free():
+    """Known trajectories given as callables are re-evaluated with ``free``
+    on every call (opty/direct_collocation.py:2916-2917)."""
+    case = cases.msd_unknown_trajectory('backward euler')
+    f_sym = list(case.traj_map.keys())[0]
+    fs = case.traj_map[f_sym]
+    traj_map = {f_sym: (lambda free: fs + free[0])}
+    col = ConstraintCollocator(case.eom, case.states, case.N, case.h,
+                               known_parameter_map=case.par_map,
+                               known_trajectory_map=traj_map,
+                               time_symbol=case.t)
+    con = col.generate_constraint_function()(case.free)
+    expected = case.expected_con.copy()
+    expected[3:] -= case.free[0]
+    np.testing.assert_allclose(con, expected, rtol=1e-12)
+    col.close()
+
+
+def test_c_abi_rejects_bad_configurations():
+    w = workloads.vyasarayani2011(101, seed=5)
+    col = _collocator(w)
+    pm = col.prepare_module()
+    cfg = runtime.ColloCfg()
+    cfg.abi_version = 99
+    with pytest.raises(ValueError):
+        runtime.ColloHandle(cfg, pm.cubin)
+    col.generate_constraint_function()
+    good = col._evaluator.handle.cfg
+    bad = runtime.ColloCfg.from_buffer_copy(good)
+    bad.P = good.P + 1
+    with pytest.raises(ValueError):
+        runtime.ColloHandle(bad, pm.cubin)
+    bad = runtime.ColloCfg.from_buffer_copy(good)
+    with pytest.raises(RuntimeError):     # not a cubin
+        runtime.ColloHandle(bad, b'not a cubin' * 100)
+    # evaluating before the known values were supplied is a state error
+    fresh = runtime.ColloHandle(runtime.ColloCfg.from_buffer_copy(good),
+                                pm.cubin)
+    with pytest.raises(RuntimeError):
+        fresh.constraints(np.zeros(fresh.free_len))
+    fresh.close()
+    col.close()

@@ -1,0 +1,386 @@
+"""CPU tests of the host side: symbol bookkeeping of the facade, the tape
+(lowering + forward-mode differentiation), the emitter (run through the
+test-only host harness and compared with the oracle), the compiled-module
+cache and the C-ABI library's exports."""
+
+import ctypes
+import math
+import os
+import re
+import subprocess
+import sys
+import tempfile
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import sympy as sm
+import sympy.physics.mechanics as me
+
+import cases
+import workloads
+from conftest import ROOT, assert_values_close, load_golden
+from host_harness import host_evaluate
+from opty_b200 import ConstraintCollocator, Problem, build, ir, runtime
+from opty_b200 import parse_free
+from opty_b200.lowering import lower_matrix
+from opty_b200.program import CollocationProgram
+from oracle.opty_oracle import OracleCollocator
+
+
+# ---------------------------------------------------------------------------
+# facade: constructor arguments, symbol sorting, discretisation
+# (restates opty/tests/test_direct_collocation.py:706-790, 1073-1110)
+# ---------------------------------------------------------------------------
+def _msd_collocator(**kw):
+    m, c, k, t = sm.symbols('m, c, k, t')
+    x, v, f = [s(t) for s in sm.symbols('x, v, f', cls=sm.Function)]
+    eom = sm.Matrix([x.diff() - v, m * v.diff() + c * v + k * x - f])
+    par_map = OrderedDict([(m, 1.0), (c, 2.0)])
+    traj_map = OrderedDict([(f, np.array([2.0, 2.5, 3.0, 3.5]))])
+    col = ConstraintCollocator(eom, (x, v), 4, 0.01,
+                               known_parameter_map=par_map,
+                               known_trajectory_map=traj_map, time_symbol=t,
+                               **kw)
+    return col, (m, c, k, t, x, v, f)
+
+
+def test_symbol_sorting_and_discrete_symbols():
+    col, (m, c, k, t, x, v, f) = _msd_collocator()
+    assert col.state_symbols == (x, v)
+    assert col.state_derivative_symbols == (x.diff(t), v.diff(t))
+    assert col.num_states == 2 and col.num_collocation_nodes == 4
+    assert col.known_parameters == (m, c)
+    assert col.unknown_parameters == (k,)
+    assert col.parameters == (m, c, k)
+    assert col.known_input_trajectories == (f,)
+    assert col.unknown_input_trajectories == ()
+    assert col.num_free == 2 * 4 + 1
+    assert col.num_constraints == 2 * 3
+    xi, vi, xp, vp, xn, vn, fi, fn = sm.symbols(
+        'xi, vi, xp, vp, xn, vn, fi, fn', real=True)
+    assert col.previous_discrete_state_symbols == (xp, vp)
+    assert col.current_discrete_state_symbols == (xi, vi)
+    assert col.next_discrete_state_symbols == (xn, vn)
+    assert col.current_discrete_specified_symbols == (fi,)
+    assert col.next_discrete_specified_symbols == (fn,)
+    assert col.time_interval_symbol == sm.Symbol('h_opty', real=True)
+
+
+def test_discretisation_formulas():
+    col, (m, c, k, t, x, v, f) = _msd_collocator()
+    xi, vi, xp, vp, xn, vn, fi, fn = sm.symbols(
+        'xi, vi, xp, vp, xn, vn, fi, fn', real=True)
+    h = col.time_interval_symbol
+    be = sm.Matrix([(xi - xp) / h - vi,
+                    m * (vi - vp) / h + c * vi + k * xi - fi])
+    assert sm.simplify(col.discrete_eom - be) == sm.zeros(2, 1)
+    col.integration_method = 'midpoint'
+    mp = sm.Matrix([(xn - xi) / h - (vi + vn) / 2,
+                    m * (vn - vi) / h + c * (vi + vn) / 2 +
+                    k * (xi + xn) / 2 - (fi + fn) / 2])
+    assert sm.simplify(col.discrete_eom - mp) == sm.zeros(2, 1)
+    with pytest.raises(ValueError):
+        col.integration_method = 'booger'
+
+
+def test_known_and_unknown_order():
+    """Known symbols keep the user's order, unknown ones are sorted by name
+    (opty/tests/test_direct_collocation.py:2042-2088)."""
+    from sympy.physics.mechanics.models import n_link_pendulum_on_cart
+    me.dynamicsymbols._t = sm.Symbol('t')
+    kane = n_link_pendulum_on_cart(n=3, cart_force=True, joint_torques=True)
+    states = kane.q.col_join(kane.u)
+    eom = kane.mass_matrix_full @ states.diff() - kane.forcing_full
+    syms = {s.name: s for s in eom.free_symbols}
+    funcs = {f.name: f for f in me.find_dynamicsymbols(eom)
+             if hasattr(f, 'name')}
+    par_map = OrderedDict([(syms['m2'], 1.0), (syms['g'], 9.81),
+                           (syms['l1'], 0.5)])
+    traj_map = OrderedDict([(funcs['T2'], np.ones(5)),
+                            (funcs['F'], np.zeros(5))])
+    col = ConstraintCollocator(eom, list(states), 5, 0.01,
+                               known_parameter_map=par_map,
+                               known_trajectory_map=traj_map)
+    assert col.known_parameters == (syms['m2'], syms['g'], syms['l1'])
+    assert [p.name for p in col.unknown_parameters] == sorted(
+        n for n in syms if n not in ('m2', 'g', 'l1', 't'))
+    assert col.known_input_trajectories == (funcs['T2'], funcs['F'])
+    assert [f.name for f in col.unknown_input_trajectories] == ['T1', 'T3']
+    rows, uniform, wrt = col._program_inputs()
+    # device rows: states, unknown inputs, known inputs
+    assert len(rows) == 8 + 2 + 2
+    assert uniform[:3] == [syms['m2'], syms['g'], syms['l1']]
+    assert uniform[-1] == col.time_interval_symbol
+
+
+def test_constructor_errors():
+    m, c, k, t = sm.symbols('m, c, k, t')
+    x, v, f = [s(t) for s in sm.symbols('x, v, f', cls=sm.Function)]
+    eom = sm.Matrix([x.diff() - v, m * v.diff() + c * v + k * x - f])
+    with pytest.raises(ValueError):
+        ConstraintCollocator(eom, (x, v), 4, 0.01, time_symbol=t,
+                             backend='fortran')
+    with pytest.raises(NotImplementedError):
+        ConstraintCollocator(eom, (x, v), 4, 0.01, time_symbol=t,
+                             backend='cython')
+    with pytest.raises(ValueError):
+        ConstraintCollocator(eom, (x, v), 4, 0.01, time_symbol=t,
+                             integration_method='simpson')
+    with pytest.raises(ValueError):
+        ConstraintCollocator(eom, (x, x), 4, 0.01, time_symbol=t)
+    with pytest.raises(ValueError):   # wrong length of a known trajectory
+        ConstraintCollocator(eom, (x, v), 4, 0.01, time_symbol=t,
+                             known_trajectory_map={f: np.ones(3)})
+    with pytest.raises(ValueError):   # state derivative without a state
+        ConstraintCollocator(eom, (x,), 4, 0.01, time_symbol=t)
+    with pytest.raises(ValueError):
+        ConstraintCollocator(eom, (x, v), 4, 0.01, time_symbol=t,
+                             cuda_options={'no_such_option': 1})
+    with pytest.raises(ValueError):   # Problem needs time derivatives
+        Problem(lambda fr: 0.0, lambda fr: fr, sm.Matrix([x - v]), (x, v), 4,
+                0.01, time_symbol=t)
+
+
+def test_instance_constraint_indexing():
+    case = cases.pendulum_variable_duration()
+    col = ConstraintCollocator(*case.collocator_args(),
+                               **case.collocator_kwargs())
+    rows, cols = col._instance_constraints_jacobian_indices()
+    assert list(rows) == [6, 7, 8, 9]
+    assert list(cols) == [0, 3, 4, 7]
+    np.testing.assert_allclose(col.eval_instance_constraints(case.free),
+                               case.expected_con[-4:])
+    np.testing.assert_allclose(
+        col.eval_instance_constraints_jacobian_values(case.free),
+        [1.0, 3.0, 4.0, 5.0])
+    th = sm.Function('theta')
+    h = case.h
+    with pytest.raises(ValueError):
+        ConstraintCollocator(case.eom, case.states, 4, h,
+                             known_parameter_map=case.par_map,
+                             instance_constraints=(th(7 * h),),
+                             time_symbol=case.t)
+
+
+def test_parse_free():
+    """opty/tests/test_utils.py parse_free cases: q = 0, 1, 2; fixed and
+    variable duration."""
+    n, N = 2, 3
+    free = np.arange(n * N + 2 * N + 2 + 1, dtype=float)
+    x, u, p, h = parse_free(free, n, 2, N, variable_duration=True)
+    assert x.shape == (2, 3) and u.shape == (2, 3)
+    assert list(p) == [12.0, 13.0] and h == 14.0
+    x, u, p = parse_free(free[:n * N + N + 1], n, 1, N)
+    assert u.shape == (3,) and list(p) == [9.0]
+    x, u, p = parse_free(free[:n * N + 2], n, 0, N)
+    assert u is None and list(p) == [6.0, 7.0]
+    assert np.shares_memory(x, free)
+
+
+# ---------------------------------------------------------------------------
+# tape: lowering and differentiation against SymPy
+# ---------------------------------------------------------------------------
+def test_tape_lowering_and_forward_jacobian_match_sympy():
+    a, b, c, d = sm.symbols('a b c d', real=True)
+    exprs = [
+        -a * b - c * d + a / 2,
+        a * b / (c * d) + sm.sqrt(c) * d**3,
+        sm.sin(a) * sm.cos(b) + sm.tan(a * b) - sm.exp(-a * a),
+        sm.log(c) * sm.atan(a) + sm.asin(a / 3) + sm.acos(b / 5),
+        sm.sinh(a) + sm.cosh(b) * sm.tanh(c) + c**sm.Rational(3, 2),
+        sm.atan2(a, c) + sm.Abs(b) + c**d + (a + b)**-2,
+        sm.Max(a, b) * sm.Min(c, d) + sm.sign(b) * a,
+        sm.Piecewise((a**2, a > b), (b * c, True)) + sm.Heaviside(b) * d,
+    ]
+    syms = [a, b, c, d]
+    rng = np.random.default_rng(0)
+    for use_cse in (True, False):
+        T = ir.Tape()
+        leaf = {s: T.vin(i) for i, s in enumerate(syms)}
+        outs = lower_matrix(T, leaf, exprs, use_sympy_cse=use_cse)
+        rows = ir.forward_jacobian(T, outs, [leaf[s] for s in syms])
+        for _ in range(3):
+            vals = [0.3 + rng.random(), -1.2 + rng.random(),
+                    1.5 + rng.random(), 0.7 + rng.random()]
+            sub = dict(zip(syms, vals))
+            got = T.evaluate(outs, vals, [])
+            for e, g in zip(exprs, got):
+                assert math.isclose(g, float(e.subs(sub)), rel_tol=1e-13,
+                                    abs_tol=1e-13)
+            for e, row in zip(exprs, rows):
+                for k, s in enumerate(syms):
+                    want = float(e.diff(s).subs(sub).evalf())
+                    node = row.get(k, T.zero)
+                    have = T.evaluate([node], vals, [])[0]
+                    assert math.isclose(have, want, rel_tol=1e-12,
+                                        abs_tol=1e-12), (e, s)
+
+
+def test_tape_simplifications():
+    T = ir.Tape()
+    x, y = T.vin(0), T.vin(1)
+    assert T.mul(x, T.zero) == T.zero
+    assert T.mul(T.one, x) == x
+    assert T.add(x, T.zero) == x
+    assert T.sub(x, x) == T.zero
+    assert T.neg(T.neg(x)) == x
+    assert T.add(x, y) == T.add(y, x)          # hash-consed, commutative
+    assert T.mul(x, y) == T.mul(y, x)
+    assert T.powi(x, 2) == T.mul(x, x)
+    assert T.op[T.div(x, T.const(4.0))] == ir.MUL   # exact power-of-two scale
+    assert T.op[T.div(x, T.const(3.0))] == ir.DIV
+    u = T.uin(0)
+    assert not T.varying[T.mul(u, u)] and T.varying[T.mul(u, x)]
+
+
+def test_program_classifies_entries_and_partitions_rows():
+    w = workloads.n_link_pendulum(3, 50)
+    col = ConstraintCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    rows, uniform, wrt = col._program_inputs()
+    prog = CollocationProgram(list(col.discrete_eom), rows, uniform, wrt)
+    assert (prog.M, prog.P, prog.R) == (8, 18, 9)
+    kinds = prog.entry_kind()
+    assert len(kinds) == 8 * 18
+    assert (prog.num_literal_entries + prog.num_invariant_entries +
+            prog.num_varying_entries) == 8 * 18
+    # kinematic rows q' - u = 0 only hold literals and +-1/h
+    assert all(k in (0, 1) for k in kinds[:4 * 18])
+    for G in (1, 2, 3, 5, 8):
+        parts = prog.partition_rows(G, col_align=2)
+        assert parts[0][0] == 0 and parts[-1][1] == prog.M
+        assert len(parts) <= G
+        for (a0, a1), (b0, b1) in zip(parts, parts[1:]):
+            assert a1 == b0 and a0 < a1
+        assert all((r0 * prog.P) % 2 == 0 for r0, _ in parts)
+
+
+# ---------------------------------------------------------------------------
+# emitter, run on the CPU through the test-only host harness, vs the oracle
+# ---------------------------------------------------------------------------
+HARNESS_WORKLOADS = [
+    ('cfg1_pendulum_swing_up_N51', lambda: workloads.pendulum_swing_up(51)),
+    ('cfg3_vyasarayani2011_N101_odd',
+     lambda: workloads.vyasarayani2011(101, seed=5)),
+    ('cfg4_standin_pendulum4_torques_N200',
+     lambda: workloads.n_link_pendulum_torques(4, 200)),
+    ('cfg2_small_pendulum10_N40',
+     lambda: workloads.n_link_pendulum(10, 40, seed=7)),
+]
+
+
+@pytest.mark.parametrize('name,make', HARNESS_WORKLOADS,
+                         ids=[f[0] for f in HARNESS_WORKLOADS])
+@pytest.mark.parametrize('groups', [1, 3])
+def test_emitted_code_matches_reference_golden(name, make, groups):
+    gold = load_golden(name)
+    w = make()
+    col = ConstraintCollocator(*w.collocator_args(), **w.collocator_kwargs(),
+                               cuda_options={'groups': groups})
+    free = w.free(col.num_free)
+    con, jac = host_evaluate(col, free)
+    M = col.num_eom
+    nn = col.num_collocation_nodes - 1
+    P = len(jac) // (nn * M)
+    assert_values_close(con, gold['con'][:M * nn])
+    assert_values_close(jac, gold['jac'][:nn * M * P], row_len=P)
+
+
+@pytest.mark.parametrize('case', cases.all_cases(), ids=lambda c: c.name)
+def test_emitted_code_known_answers(case):
+    col = ConstraintCollocator(*case.collocator_args(),
+                               **case.collocator_kwargs())
+    con, jac = host_evaluate(col, case.free)
+    np.testing.assert_allclose(con, case.expected_con[:len(con)], rtol=1e-12,
+                               atol=1e-9)
+    np.testing.assert_allclose(jac, case.expected_jac[:len(jac)], rtol=1e-12,
+                               atol=1e-9)
+
+
+# ---------------------------------------------------------------------------
+# native pieces: module compilation + cache, C-ABI exports
+# ---------------------------------------------------------------------------
+def test_module_compiles_for_sm100a_and_is_cached():
+    w = workloads.vyasarayani2011(101, seed=5)
+    with tempfile.TemporaryDirectory() as tmp:
+        col = ConstraintCollocator(*w.collocator_args(),
+                                   **w.collocator_kwargs(), tmp_dir=tmp)
+        first = col.prepare_module()
+        assert not first.cache_hit and len(first.cubin) > 1000
+        second = col.prepare_module()
+        assert second.cache_hit and second.cubin == first.cubin
+        sass = subprocess.run(['cuobjdump', '-sass', first.cubin_path],
+                              capture_output=True, text=True).stdout
+        assert 'sm_100a' in sass
+        assert 'UTMALDG' in sass          # TMA tile load of the trajectory
+        assert 'UTMASTG' in sass          # TMA tile store of the Jacobian
+        # a module emitted without TMA has neither
+        col2 = ConstraintCollocator(
+            *w.collocator_args(), **w.collocator_kwargs(), tmp_dir=tmp,
+            cuda_options={'tma_load': False, 'tma_store': False})
+        plain = col2.prepare_module()
+        sass2 = subprocess.run(['cuobjdump', '-sass', plain.cubin_path],
+                               capture_output=True, text=True).stdout
+        assert 'UTMASTG' not in sass2 and 'UTMALDG' not in sass2
+
+
+def test_compile_failure_raises_import_error():
+    """Build failures surface as ImportError with the compiler's stderr
+    (opty/utils.py:909-916, pinned by opty/tests/test_utils.py:333-336)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        with pytest.raises(ImportError) as err:
+            build.compile_module('this is not CUDA;', build.module_flags(),
+                                 cache_dir=tmp)
+        assert 'STDERR' in str(err.value)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    lib = runtime.load_library()
+    header = open(os.path.join(ROOT, 'include', 'opty_b200.h')).read()
+    declared = set(re.findall(r'\b(opty_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(runtime.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.opty_b200_abi_version() == runtime.ABI_VERSION
+
+
+def test_c_abi_config_struct_layout_matches_header():
+    src = ('#include "opty_b200.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+           'int main(void){printf("%zu %zu %zu", sizeof(opty_colloc_cfg), '
+           'offsetof(opty_colloc_cfg, group_col0), '
+           'offsetof(opty_colloc_cfg, h)); return 0;}')
+    with tempfile.TemporaryDirectory() as tmp:
+        c = os.path.join(tmp, 'sz.c')
+        open(c, 'w').write(src)
+        exe = os.path.join(tmp, 'sz')
+        subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), '-o', exe,
+                        c], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True).stdout
+    size, off_g, off_h = (int(v) for v in out.split())
+    assert size == ctypes.sizeof(runtime.ColloCfg)
+    assert off_g == runtime.ColloCfg.group_col0.offset
+    assert off_h == runtime.ColloCfg.h.offset
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """The product path fails loudly when no CUDA device is present."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    w = workloads.vyasarayani2011(101, seed=5)
+    col = ConstraintCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    with pytest.raises(RuntimeError) as err:
+        col.generate_constraint_function()
+    assert 'CUDA' in str(err.value)
+    with pytest.raises(RuntimeError):
+        col.jacobian_indices()
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, 'opty_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert 'oracle' not in text.lower(), fn
+                assert 'host_harness' not in text, fn

@@ -140,7 +140,7 @@ def n_link_pendulum_torques(links=4, num_nodes=2000, method='backward euler',
             continue                      # left unknown: r = 2
         par_map[c] = 9.81 if c.name == 'g' else 0.5 + rng.random()
     force = [f for f in me.find_dynamicsymbols(eom)
-             if f.name == 'F'][0]
+             if getattr(f, 'name', None) == 'F'][0]
     time = np.linspace(0.0, 1.0, num_nodes)
     traj_map = OrderedDict([(force, np.sin(3.0 * time))])
     h = sm.Symbol('h', real=True)
