@@ -128,9 +128,12 @@ int opty_colloc_device_buffers(opty_colloc_t* h, void** traj, int64_t* ldt, void
                                void** uni);
 
 /* Restricts Jacobian device->host copies to the column ranges
- * [col_begin[i], col_end[i]) of every node block (columns outside are
- * literal constants that `fill` != NULL pre-writes once into the pinned
- * Jacobian buffer).  `num_ranges` = 0 restores full copies. */
+ * [col_begin[i], col_end[i]) of every node block.  Columns outside the ranges
+ * must hold values that do not change between calls (literals, or functions
+ * of known parameters only); they reach the pinned Jacobian buffer through
+ * one full copy after this call / after opty_colloc_set_known (or from
+ * `fill`, a K-entry per-node pattern, if given).  `num_ranges` = 0 restores
+ * full copies. */
 int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t* col_begin,
                                 const int32_t* col_end, const double* fill);
 

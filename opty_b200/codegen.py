@@ -158,12 +158,15 @@ def choose_tile_cols(requested):
 
 
 def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
-                min_blocks_per_sm=4, tma_load=True, tma_store=True):
+                min_blocks_per_sm=4, tma_load=True, tma_store=True,
+                block_sync=False, debug_nostore=False):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(r0, r1)`` EOM row ranges)."""
     T = prog.tape
     M, P, K, R = prog.M, prog.P, prog.K, prog.R
     C = choose_tile_cols(tile_cols)
+    if warps_per_block > 4 and warps_per_block % 4:
+        raise ValueError('warps_per_block above 4 must be a multiple of 4')
     ninv = len(prog.inv_nodes)
 
     out = []
@@ -182,6 +185,9 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     w('#define OPTY_MIN_BLOCKS {}'.format(min_blocks_per_sm))
     w('#define OPTY_TMA_LOAD {}'.format(1 if tma_load else 0))
     w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
+    w('#define OPTY_BLOCK_SYNC {}'.format(1 if block_sync else 0))
+    if debug_nostore:
+        w('#define OPTY_DEBUG_NOSTORE 1')
     w('#include "colloc_kernel.cuh"')
     w('')
 
@@ -278,6 +284,7 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         'min_blocks_per_sm': min_blocks_per_sm,
         'tma_load': bool(tma_load),
         'tma_store': bool(tma_store),
+        'block_sync': bool(block_sync),
         'method': method,
         'entry_kind': prog.entry_kind(),
         'stats': prog.stats(),

@@ -32,10 +32,26 @@
 #include "colloc_params.h"
 
 #define OPTY_THREADS (OPTY_WARPS * 32)
-// columns of the staged trajectory tile: one per node of the block plus the
-// right neighbour, rounded up to an even count (TMA rows are 16-byte multiples)
-#define OPTY_XW (OPTY_THREADS + 2)
+// The block's slice of the trajectory matrix is staged in segments of
+// OPTY_XSEG nodes; a segment holds one column per node plus the right
+// neighbour, rounded up to an even count (TMA rows are 16-byte multiples, TMA
+// boxes at most 256 elements wide).  Blocks wider than 128 threads use several
+// overlapping segments.
+#if OPTY_THREADS <= 128
+#define OPTY_XSEG OPTY_THREADS
+#else
+#define OPTY_XSEG 128
+#endif
+#define OPTY_XBOX (OPTY_XSEG + 2)
+#define OPTY_NSEG (OPTY_THREADS / OPTY_XSEG)
+#define OPTY_XSEG_BYTES (((OPTY_R * OPTY_XBOX * 8) + 127) / 128 * 128)
 #define OPTY_TILE_DOUBLES (32 * OPTY_C)
+#ifndef OPTY_BLOCK_SYNC
+#define OPTY_BLOCK_SYNC 0
+#endif
+#ifndef OPTY_DEBUG_NOSTORE
+#define OPTY_DEBUG_NOSTORE 0   // measurement aid: skip the Jacobian tile stores
+#endif
 
 struct OptyTmaps {
   CUtensorMap in;                  // traj as {cols, R}
@@ -47,7 +63,7 @@ __constant__ double opty_ci[OPTY_NINV];
 #define CI(k) opty_ci[k]
 
 struct OptyCtx {
-  const double* xs;     // &xin[threadIdx.x]; row pitch OPTY_XW
+  const double* xs;     // this lane's column in its staged segment; row pitch OPTY_XBOX
   double* con;          // &con[node]
   double* trow0;        // this lane's row in tile buffer 0
   double* trow1;        // this lane's row in tile buffer 1
@@ -111,8 +127,8 @@ static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map,
 }
 
 // trajectory value of row r at this lane's node (A) and at the next node (B)
-#define XA(r) ctx.xs[(r) * OPTY_XW]
-#define XB(r) ctx.xs[(r) * OPTY_XW + 1]
+#define XA(r) ctx.xs[(r) * OPTY_XBOX]
+#define XB(r) ctx.xs[(r) * OPTY_XBOX + 1]
 
 #define OPTY_CON(j, val)                                   \
   do {                                                     \
@@ -134,14 +150,25 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   // lane issues the tile store; at most one older store may still be reading
   // its buffer (the other one) when the warp continues
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#if OPTY_BLOCK_SYNC
+  // all warps of the block run the same group: meeting here keeps them on the
+  // same instruction-cache lines (the kernel is instruction-fetch bound
+  // otherwise)
+  __syncthreads();
+#else
   __syncwarp();
-  if (ctx.lane == 0) {
+#endif
+  if (ctx.lane == 0 && ctx.node < ctx.n_nodes && !OPTY_DEBUG_NOSTORE) {
     opty_tma_store_2d(&ctx.tm->out[G], tile, Q * OPTY_C, ctx.node);
     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
   }
   __syncwarp();
 #else
+#if OPTY_BLOCK_SYNC
+  __syncthreads();
+#else
   __syncwarp();
+#endif
   const int rows = min(32, ctx.n_nodes - ctx.node);
   for (int r = 0; r < rows; ++r) {
     double* dst = ctx.jac + (long long)(ctx.node + r) * OPTY_K + COL0 + Q * OPTY_C;
@@ -167,10 +194,10 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   } while (0)
 #endif
 
-// dynamic shared memory: [WARPS][2][32][C] Jacobian tiles | [R][XW] trajectory
-// tile | mbarrier
+// dynamic shared memory: [WARPS][2][32][C] Jacobian tiles | [NSEG][R][XBOX]
+// trajectory segments | mbarrier
 #define OPTY_SMEM_TILES_BYTES (OPTY_WARPS * 2 * OPTY_TILE_DOUBLES * 8)
-#define OPTY_SMEM_XIN_BYTES (((OPTY_R * OPTY_XW * 8) + 127) / 128 * 128)
+#define OPTY_SMEM_XIN_BYTES (OPTY_NSEG * OPTY_XSEG_BYTES)
 #define OPTY_SMEM_BYTES (OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES + 128)
 
 #if OPTY_TMA_LOAD
@@ -178,24 +205,34 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   if (threadIdx.x == 0) opty_mbar_init(bar, 1);                                         \
   __syncthreads();                                                                      \
   if (threadIdx.x == 0) {                                                               \
-    opty_mbar_expect_tx(bar, OPTY_R * OPTY_XW * 8);                                     \
-    opty_tma_load_2d(xin, &tm.in, block_node0, 0, bar);                                 \
+    opty_mbar_expect_tx(bar, OPTY_NSEG * OPTY_R * OPTY_XBOX * 8);                       \
+    for (int sgm = 0; sgm < OPTY_NSEG; ++sgm)                                           \
+      opty_tma_load_2d(xin_bytes + sgm * OPTY_XSEG_BYTES, &tm.in, block_node0 + sgm * OPTY_XSEG, 0, bar); \
   }                                                                                     \
   opty_mbar_wait(bar, 0);
 #else
 #define OPTY_STAGE_INPUT()                                                              \
-  for (int r = 0; r < OPTY_R; ++r)                                                      \
-    for (int c = threadIdx.x; c < OPTY_XW; c += OPTY_THREADS) {                         \
-      const int col = block_node0 + c;                                                  \
-      xin[r * OPTY_XW + c] = (col < p.n_cols) ? __ldg(p.traj + (long long)r * p.ldt + col) : 0.0; \
-    }                                                                                   \
+  for (int sgm = 0; sgm < OPTY_NSEG; ++sgm) {                                           \
+    double* dstseg = reinterpret_cast<double*>(xin_bytes + sgm * OPTY_XSEG_BYTES);      \
+    for (int r = 0; r < OPTY_R; ++r)                                                    \
+      for (int c = threadIdx.x; c < OPTY_XBOX; c += OPTY_THREADS) {                     \
+        const int col = block_node0 + sgm * OPTY_XSEG + c;                              \
+        dstseg[r * OPTY_XBOX + c] = (col < p.n_cols) ? __ldg(p.traj + (long long)r * p.ldt + col) : 0.0; \
+      }                                                                                 \
+  }                                                                                     \
   __syncthreads();
+#endif
+
+#if OPTY_BLOCK_SYNC
+#define OPTY_SKIP_IDLE_WARP()
+#else
+#define OPTY_SKIP_IDLE_WARP() if (ctx.node >= p.n_nodes) return;
 #endif
 
 #define OPTY_PROLOGUE()                                                                 \
   extern __shared__ __align__(128) unsigned char opty_smem[];                           \
   double* tiles = reinterpret_cast<double*>(opty_smem);                                 \
-  double* xin = reinterpret_cast<double*>(opty_smem + OPTY_SMEM_TILES_BYTES);           \
+  unsigned char* xin_bytes = opty_smem + OPTY_SMEM_TILES_BYTES;                         \
   uint64_t* bar = reinterpret_cast<uint64_t*>(opty_smem + OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES); \
   const int block_node0 = blockIdx.x * OPTY_THREADS;                                    \
   (void)bar;                                                                            \
@@ -205,7 +242,8 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   ctx.node = block_node0 + (threadIdx.x & ~31);                                         \
   ctx.n_nodes = p.n_nodes;                                                              \
   ctx.active = (block_node0 + (int)threadIdx.x) < p.n_nodes;                            \
-  ctx.xs = xin + threadIdx.x;                                                           \
+  ctx.xs = reinterpret_cast<const double*>(xin_bytes + (threadIdx.x / OPTY_XSEG) * OPTY_XSEG_BYTES) + \
+           (threadIdx.x % OPTY_XSEG);                                                   \
   ctx.con = p.con + block_node0 + threadIdx.x;                                          \
   ctx.ldc = p.ldc;                                                                      \
   ctx.tile0 = tiles + (threadIdx.x >> 5) * 2 * OPTY_TILE_DOUBLES;                       \
@@ -213,4 +251,4 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   ctx.trow1 = ctx.trow0 + OPTY_TILE_DOUBLES;                                            \
   ctx.jac = p.jac;                                                                      \
   ctx.tm = &tm;                                                                         \
-  if (ctx.node >= p.n_nodes) return;
+  OPTY_SKIP_IDLE_WARP()

@@ -176,6 +176,7 @@ struct opty_colloc {
   bool inv_dirty = true;
   bool evaluated = false;
   bool con_fetched = false, jac_fetched = false;
+  bool full_fetch_needed = true;  // constant Jacobian columns not yet on the host
 
   std::vector<int32_t> d2h_begin, d2h_end;
   unsigned smem_bytes = 0;
@@ -206,8 +207,9 @@ int build_tmaps(opty_colloc* h, int slot) {
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(blob.data());
   int rc;
   if (c.tma_load) {
-    const uint32_t xw = 32u * c.warps_per_block + 2u;
-    if ((rc = encode_2d(&maps[0], h->d_traj, (uint64_t)h->ncols, (uint64_t)h->R, (uint64_t)h->ldt * 8, xw,
+    const uint32_t threads = 32u * c.warps_per_block;
+    const uint32_t xbox = (threads <= 128u ? threads : 128u) + 2u;
+    if ((rc = encode_2d(&maps[0], h->d_traj, (uint64_t)h->ncols, (uint64_t)h->R, (uint64_t)h->ldt * 8, xbox,
                         (uint32_t)h->R)))
       return rc;
   }
@@ -294,7 +296,8 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   if (cfg->node_lo < 0 || cfg->node_hi > cfg->N - 1 || cfg->node_lo >= cfg->node_hi)
     return fail(OPTY_ERR_ARG, "invalid node range");
   if (cfg->num_groups < 1 || cfg->num_groups > OPTY_MAX_GROUPS) return fail(OPTY_ERR_ARG, "invalid group count");
-  if (cfg->warps_per_block < 1 || cfg->warps_per_block > 32 || cfg->tile_cols < 2 || (cfg->tile_cols & 1) ||
+  if (cfg->warps_per_block < 1 || cfg->warps_per_block > 32 ||
+      (cfg->warps_per_block > 4 && cfg->warps_per_block % 4 != 0) || cfg->tile_cols < 2 || (cfg->tile_cols & 1) ||
       cfg->tile_cols > 256)
     return fail(OPTY_ERR_ARG, "invalid kernel geometry");
   if (cfg->out_ring < 1 || cfg->out_ring > 64) return fail(OPTY_ERR_ARG, "invalid out_ring");
@@ -390,8 +393,10 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   CREATE_RT(cudaHostAlloc(&h->h_jac, ((size_t)h->nn * h->K + cfg->jac_tail) * 8, cudaHostAllocDefault));
 
   const unsigned tiles_bytes = (unsigned)cfg->warps_per_block * 2u * 32u * cfg->tile_cols * 8u;
-  const unsigned xw = 32u * cfg->warps_per_block + 2u;
-  const unsigned xin_bytes = (unsigned)round_up((int64_t)h->R * xw * 8, 128);
+  const unsigned threads = 32u * cfg->warps_per_block;
+  const unsigned xseg = threads <= 128u ? threads : 128u;
+  const unsigned nseg = threads / xseg;
+  const unsigned xin_bytes = nseg * (unsigned)round_up((int64_t)h->R * (xseg + 2u) * 8, 128);
   h->smem_bytes = tiles_bytes + xin_bytes + 128u;
   if (h->smem_bytes > 227u * 1024u) {
     opty_colloc_destroy(h);
@@ -441,6 +446,7 @@ int opty_colloc_set_known(opty_colloc_t* h, const double* traj, const double* pa
   h->known_set = true;
   h->inv_dirty = true;
   h->evaluated = false;
+  h->full_fetch_needed = true;
   return OPTY_OK;
 }
 
@@ -486,8 +492,11 @@ int opty_colloc_jacobian(opty_colloc_t* h, const double* free_host, double* jac_
   if (!h->evaluated && (rc = launch_eval(h))) return rc;
   const size_t bytes = (size_t)h->nn * h->K * 8;
   if (!h->jac_fetched) {
-    if (h->d2h_begin.empty()) {
+    if (h->d2h_begin.empty() || h->full_fetch_needed) {
+      // first fetch (and every fetch without column ranges): the whole block,
+      // which also brings the constant columns to the host once
       RT_CHECK(cudaMemcpyAsync(h->h_jac, h->d_jac[h->ring], bytes, cudaMemcpyDeviceToHost, h->stream));
+      h->full_fetch_needed = false;
     } else {
       for (size_t i = 0; i < h->d2h_begin.size(); ++i) {
         const int b = h->d2h_begin[i], e = h->d2h_end[i];
@@ -540,6 +549,7 @@ int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t*
   h->d2h_begin.swap(b);
   h->d2h_end.swap(e);
   h->jac_fetched = false;
+  if (!fill) h->full_fetch_needed = true;
   return OPTY_OK;
 }
 

@@ -56,6 +56,8 @@ DEFAULT_CUDA_OPTIONS = {
     'maxrregcount': None,
     'tma_load': True,
     'tma_store': True,
+    'block_sync': False,        # __syncthreads at every tile flush
+    'debug_nostore': False,     # measurement aid: skip Jacobian tile stores
     'out_ring': 1,              # device output sets to rotate through
     'use_sympy_cse': True,
     'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
@@ -559,7 +561,9 @@ class _PreparedModule(object):
             tile_cols=opts['tile_cols'],
             warps_per_block=opts['warps_per_block'],
             min_blocks_per_sm=opts['min_blocks_per_sm'],
-            tma_load=tma_load, tma_store=tma_store)
+            tma_load=tma_load, tma_store=tma_store,
+            block_sync=opts['block_sync'],
+            debug_nostore=opts['debug_nostore'])
         flags = build.module_flags(fmad=opts['fmad'],
                                    maxrregcount=opts['maxrregcount'])
         logger.info('Compiling the constraint and Jacobian kernels.')
@@ -656,23 +660,28 @@ class _CudaEvaluator(object):
         self.handle.set_known(traj, params)
 
     def _setup_constant_elision(self):
-        """Jacobian columns whose value is a literal for every node (about
-        half of them at the 10-link pendulum) are written to the
-        pinned host buffer once; device->host copies then skip the leading and
-        trailing literal-only column ranges."""
+        """Jacobian columns whose value cannot change between calls --
+        literals, and node-invariant entries when there is no free parameter
+        or time interval (about half of all columns at the 10-link pendulum,
+        SURVEY.md §7) -- are copied to the pinned host buffer once, with the
+        first full device->host copy.  Later copies only move the column
+        ranges that hold call-dependent entries."""
+        col = self.col
         kinds = np.array(self.meta['entry_kind'])
-        tape = self.program.tape
-        fill = np.array([tape.val[e] if tape.op[e] == 0 else 0.0
-                         for row in self.program.jac for e in row])
-        nonlit = np.nonzero(kinds != 0)[0]
-        if len(nonlit) == 0:
+        frozen_invariants = (col.num_unknown_parameters == 0 and
+                             not col._variable_duration)
+        changing = kinds == 2
+        if not frozen_invariants:
+            changing |= kinds == 1
+        idx = np.nonzero(changing)[0]
+        if len(idx) == 0:
             ranges = [(0, 1)]
         else:
-            # merge runs of non-literal columns separated by short gaps
-            min_gap = 64
+            # merge runs of changing columns separated by short gaps
+            min_gap = 32
             ranges = []
-            start = prev = int(nonlit[0])
-            for c in nonlit[1:]:
+            start = prev = int(idx[0])
+            for c in idx[1:]:
                 c = int(c)
                 if c - prev > min_gap:
                     ranges.append((start, prev + 1))
@@ -682,7 +691,7 @@ class _CudaEvaluator(object):
             if len(ranges) > 8:
                 ranges = [(ranges[0][0], ranges[-1][1])]
         self.d2h_ranges = ranges
-        self.handle.set_d2h_columns(ranges, fill)
+        self.handle.set_d2h_columns(ranges, None)
 
     # callbacks --------------------------------------------------------
     def _check_free(self, free):
