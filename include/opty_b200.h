@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define OPTY_B200_ABI_VERSION 1
+#define OPTY_B200_ABI_VERSION 2
 #define OPTY_MAX_GROUPS 64
 
 #define OPTY_OK 0
@@ -63,15 +63,17 @@ typedef struct opty_colloc_cfg {
   int32_t P;                /* partials per equation (2n+q+r+s or 2n+2q+r+s) */
   int32_t method;           /* OPTY_BACKWARD_EULER / OPTY_MIDPOINT */
   int32_t num_inv;          /* entries of the node-invariant table */
-  int32_t num_groups;       /* output groups (grid.y) */
+  int32_t num_groups;       /* output groups */
+  int32_t num_derived;      /* D: derived rows written by the pre-pass kernel */
   int32_t tile_cols;        /* C: columns of the Jacobian staging tile */
   int32_t warps_per_block;
+  int32_t pre_groups;       /* grid.y of the pre-pass kernel (groups of derived rows) */
+  int32_t tile_bufs;        /* staging tiles per warp (2..4) */
   int32_t tma_load;         /* module was emitted with TMA input staging */
   int32_t tma_store;        /* module was emitted with TMA Jacobian stores */
   int32_t out_ring;         /* number of device output sets to rotate (>=1) */
   int32_t con_tail;         /* extra host slots after the M*(N-1) residuals */
   int32_t jac_tail;         /* extra host slots after the (N-1)*M*P partials */
-  int32_t reserved0;
   int32_t group_col0[OPTY_MAX_GROUPS];   /* first Jacobian column of group g */
   int32_t group_ncols[OPTY_MAX_GROUPS];  /* number of columns of group g */
   double h;                 /* fixed node time interval (ignored when s=1) */

@@ -119,6 +119,12 @@ def compile_module(source, flags, cache_dir=None, show_compile_output=False,
         cmd.insert(2, '-v')
     logger.info('Compiling the collocation module %s', src_path)
     proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0 and 'Segmentation fault' in proc.stderr:
+        # ptxas 12.9 occasionally crashes on very long straight-line bodies
+        # under tight register caps at -O3; its -O2 pipeline gets through
+        logger.warning('ptxas crashed at -O3, retrying with -Xptxas -O2')
+        proc = subprocess.run(cmd[:1] + ['-Xptxas', '-O2'] + cmd[1:],
+                              capture_output=True, text=True)
     if show_compile_output:
         print(proc.stdout)
         print(proc.stderr)

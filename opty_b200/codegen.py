@@ -10,14 +10,20 @@ contains
     (functions of the parameters and the time interval only) into a table that
     the host runtime copies to ``__constant__`` memory,
 
+``opty_colloc_pre``
+    pre-pass, one thread per node: evaluates the expensive sub-expressions
+    that several output groups share (sines / cosines of the joint angles at
+    the 10-link pendulum) once per node into *derived rows* appended to the
+    trajectory matrix,
+
 ``opty_colloc_eval``
-    the hot kernel: ``grid = (ceil(nodes / (32*W)), groups)``.  A warp owns 32
-    consecutive collocation nodes (lane = node) and one output group (a
-    contiguous range of EOM rows); it stages its slice of the trajectory
-    matrix in shared memory with one TMA tile load, runs the group's
-    straight-line float64 code, writes the residuals eom-major and streams the
-    node-major Jacobian block through a double-buffered shared-memory tile that
-    is drained by TMA tile stores.
+    the hot kernel, persistent: one block slot per SM x ``min_blocks``.  A
+    warp owns 32 consecutive collocation nodes (lane = node) of one output
+    group (a contiguous range of EOM rows) per tile; it stages the tile's
+    slice of the trajectory matrix in shared memory with TMA tile loads, runs
+    the group's straight-line float64 code, writes the residuals eom-major and
+    streams the node-major Jacobian block through a double-buffered
+    shared-memory tile that is drained by TMA tile stores.
 
 The skeleton (staging, tiles, TMA, flush) is hand written in
 ``csrc/colloc_kernel.cuh``; only the arithmetic bodies and sizes come from
@@ -28,7 +34,7 @@ import os
 
 from . import ir
 
-EMITTER_VERSION = 3
+EMITTER_VERSION = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 KERNEL_HEADER = os.path.join(_HERE, 'csrc', 'colloc_kernel.cuh')
@@ -48,12 +54,19 @@ def _lit(v):
 
 class _BodyWriter(object):
     """Emits straight-line code for tape nodes on demand (depth-first from the
-    outputs, so temporaries are defined close to their first use)."""
+    outputs, so temporaries are defined close to their first use).
 
-    def __init__(self, prog, varying_ctx):
+    ``mode``: ``'inv'`` single-thread invariants kernel, ``'pre'`` pre-pass
+    kernel (trajectory values from global memory), ``'main'`` group bodies
+    (trajectory values and derived rows from the staged shared-memory tile).
+    """
+
+    def __init__(self, prog, mode, derived_index=None):
         self.prog = prog
         self.T = prog.tape
-        self.varying_ctx = varying_ctx   # True: main kernel, False: inv kernel
+        self.mode = mode
+        self.varying_ctx = mode != 'inv'
+        self.derived_index = derived_index or {}
         self.done = set()
         self.lines = []
         self.num_ops = 0
@@ -66,9 +79,14 @@ class _BodyWriter(object):
         if self.varying_ctx:
             if o == ir.VIN:
                 slot = T.a[i]
+                if self.mode == 'pre':
+                    return '{}({})'.format('GB' if slot & 1 else 'GA',
+                                           slot >> 1)
                 return '{}({})'.format('XB' if slot & 1 else 'XA', slot >> 1)
             if not T.varying[i]:
                 return 'CI({})'.format(self.prog.inv_index[i])
+            if self.mode == 'main' and i in self.derived_index:
+                return 'XD({})'.format(self.derived_index[i])
             return 'v{}'.format(i)
         if o == ir.UIN:
             return 'uni[{}]'.format(T.a[i])
@@ -81,12 +99,15 @@ class _BodyWriter(object):
         varying = T.varying
         done = self.done
         vctx = self.varying_ctx
+        derived = self.derived_index if self.mode == 'main' else {}
 
         def is_leaf(i):
             o = op_[i]
             if o <= ir.UIN:
                 return True
             if vctx and not varying[i]:
+                return True
+            if i in derived:
                 return True
             return i in done
 
@@ -159,15 +180,19 @@ def choose_tile_cols(requested):
 
 def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 min_blocks_per_sm=4, tma_load=True, tma_store=True,
-                block_sync=False, debug_nostore=False):
+                derived=(), debug_nostore=False, tile_bufs=2):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
-    (list of ``(r0, r1)`` EOM row ranges)."""
+    (list of ``(r0, r1)`` EOM row ranges).  ``derived`` lists the tape ids
+    that the pre-pass kernel evaluates once per node into derived rows."""
     T = prog.tape
     M, P, K, R = prog.M, prog.P, prog.K, prog.R
     C = choose_tile_cols(tile_cols)
     if warps_per_block > 4 and warps_per_block % 4:
         raise ValueError('warps_per_block above 4 must be a multiple of 4')
     ninv = len(prog.inv_nodes)
+    derived = list(derived)
+    derived_index = {nid: k for k, nid in enumerate(derived)}
+    D = len(derived)
 
     out = []
     w = out.append
@@ -177,6 +202,7 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     w('#define OPTY_P {}'.format(P))
     w('#define OPTY_K {}'.format(K))
     w('#define OPTY_R {}'.format(R))
+    w('#define OPTY_D {}'.format(D))
     w('#define OPTY_C {}'.format(C))
     w('#define OPTY_NGROUPS {}'.format(len(groups)))
     w('#define OPTY_NINV {}'.format(max(ninv, 1)))
@@ -185,14 +211,14 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     w('#define OPTY_MIN_BLOCKS {}'.format(min_blocks_per_sm))
     w('#define OPTY_TMA_LOAD {}'.format(1 if tma_load else 0))
     w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
-    w('#define OPTY_BLOCK_SYNC {}'.format(1 if block_sync else 0))
+    w('#define OPTY_NBUF {}'.format(int(tile_bufs)))
     if debug_nostore:
-        w('#define OPTY_DEBUG_NOSTORE 1')
+        w('#define OPTY_DEBUG_NOSTORE {}'.format(int(debug_nostore)))
     w('#include "colloc_kernel.cuh"')
     w('')
 
     # ---- invariants kernel -------------------------------------------
-    bw = _BodyWriter(prog, varying_ctx=False)
+    bw = _BodyWriter(prog, 'inv')
     for nid in prog.inv_nodes:
         bw.need(nid)
     w('extern "C" __global__ void opty_colloc_inv('
@@ -207,10 +233,41 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     w('')
     inv_ops = bw.num_ops
 
+    # ---- pre-pass kernel: derived rows, grid.y = groups of derived rows ---
+    # rows that share their argument (sin / cos of the same angle) stay
+    # together so that the argument is computed once
+    pre_chunks = []
+    by_arg = {}
+    for k, nid in enumerate(derived):
+        by_arg.setdefault(T.a[nid], []).append(k)
+    for ks in by_arg.values():
+        pre_chunks.append(ks)
+    pre_groups = len(pre_chunks)
+    w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
+    w('opty_colloc_pre(const OptyParams p)')
+    w('{')
+    w('  OPTY_PRE_BEGIN();')
+    w('  switch (opty_pg) {')
+    pre_ops = 0
+    for pg, ks in enumerate(pre_chunks):
+        bw = _BodyWriter(prog, 'pre')
+        for k in ks:
+            bw.need(derived[k])
+            bw.lines.append('OPTY_DRV({}, {});'.format(k, bw.ref(derived[k])))
+        w('    case {}: {{'.format(pg))
+        for line in bw.lines:
+            w('      ' + line)
+        w('    } break;')
+        pre_ops += bw.num_ops
+    w('    default: break;')
+    w('  }')
+    w('}')
+    w('')
+
     # ---- group bodies --------------------------------------------------
     group_meta = []
     for g, (r0, r1) in enumerate(groups):
-        bw = _BodyWriter(prog, varying_ctx=True)
+        bw = _BodyWriter(prog, 'main', derived_index)
         body = bw.lines
         col0 = r0 * P
         ncols = (r1 - r0) * P
@@ -237,11 +294,12 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                     pending = (tc, bw.ref(e))
                 elif pending is not None:
                     body.append('OPTY_JS2({}, {}, {}, {});'.format(
-                        chunk & 1, pending[0], pending[1], bw.ref(e)))
+                        chunk % tile_bufs, pending[0], pending[1],
+                        bw.ref(e)))
                     pending = None
                 else:
                     body.append('OPTY_JS1({}, {}, {});'.format(
-                        chunk & 1, tc, bw.ref(e)))
+                        chunk % tile_bufs, tc, bw.ref(e)))
                 cc += 1
                 if cc % C == 0 and pending is None:
                     flush(C)
@@ -258,33 +316,44 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         group_meta.append({'rows': [r0, r1], 'col0': col0, 'ncols': ncols,
                            'ops': bw.num_ops, 'chunks': chunk})
 
+    # blockIdx.y -> group: most expensive groups are launched first
+    order = sorted(range(len(groups)),
+                   key=lambda g: -(20 * group_meta[g]['ops'] +
+                                   43 * group_meta[g]['ncols']))
+    w('__device__ const int opty_group_order[OPTY_NGROUPS] = {{{}}};'.format(
+        ', '.join(str(g) for g in order)))
+    w('')
     w('extern "C" __global__ void __launch_bounds__(OPTY_THREADS, '
       'OPTY_MIN_BLOCKS)')
     w('opty_colloc_eval(const __grid_constant__ OptyTmaps tm, '
       'const OptyParams p)')
     w('{')
-    w('  OPTY_PROLOGUE();')
-    w('  switch (blockIdx.y) {')
+    w('  OPTY_KERNEL_BEGIN()')
+    w('  switch (opty_g) {')
     for g in range(len(groups)):
         w('    case {}: opty_group_{}(ctx); break;'.format(g, g))
     w('    default: break;')
     w('  }')
+    w('  OPTY_KERNEL_END()')
     w('}')
     w('')
 
     meta = {
         'emitter_version': EMITTER_VERSION,
-        'M': M, 'P': P, 'K': K, 'R': R, 'C': C,
+        'M': M, 'P': P, 'K': K, 'R': R, 'C': C, 'D': D,
         'num_groups': len(groups),
         'groups': group_meta,
         'num_inv': ninv,
         'num_uniform': prog.num_uniform,
         'inv_ops': inv_ops,
+        'pre_ops': pre_ops,
+        'pre_groups': pre_groups,
+        'group_order': order,
         'warps_per_block': warps_per_block,
         'min_blocks_per_sm': min_blocks_per_sm,
         'tma_load': bool(tma_load),
         'tma_store': bool(tma_store),
-        'block_sync': bool(block_sync),
+        'tile_bufs': int(tile_bufs),
         'method': method,
         'entry_kind': prog.entry_kind(),
         'stats': prog.stats(),

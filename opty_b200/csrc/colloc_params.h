@@ -3,11 +3,11 @@
 #pragma once
 
 struct OptyParams {
-  const double* traj;   // [R][ldt] trajectory matrix (states, unknown inputs, known inputs)
-  double* con;          // [M][ldc] residuals, eom-major
-  double* jac;          // [nodes][K] partials, node-major
+  double* traj;   // [R + D][ldt] trajectory matrix + derived rows
+  double* con;    // [M][ldc] residuals, eom-major
+  double* jac;    // [nodes][K] partials, node-major
   long long ldt;
   long long ldc;
-  int n_nodes;          // constraint nodes in this launch (N - 1 or a shard of them)
-  int n_cols;           // valid trajectory columns (n_nodes + 1)
+  int n_nodes;    // constraint nodes in this launch (N - 1 or a shard of them)
+  int n_cols;     // valid trajectory columns (n_nodes + 1)
 };

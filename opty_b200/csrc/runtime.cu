@@ -153,6 +153,10 @@ struct opty_colloc {
   CUmodule mod = nullptr;
   CUfunction f_eval = nullptr;
   CUfunction f_inv = nullptr;
+  CUfunction f_pre = nullptr;
+  int num_sms = 0;
+  int RD = 0;          // trajectory rows incl. derived rows
+  int n_tiles = 0;
   CUdeviceptr ci_sym = 0;
   size_t ci_bytes = 0;
 
@@ -209,8 +213,8 @@ int build_tmaps(opty_colloc* h, int slot) {
   if (c.tma_load) {
     const uint32_t threads = 32u * c.warps_per_block;
     const uint32_t xbox = (threads <= 128u ? threads : 128u) + 2u;
-    if ((rc = encode_2d(&maps[0], h->d_traj, (uint64_t)h->ncols, (uint64_t)h->R, (uint64_t)h->ldt * 8, xbox,
-                        (uint32_t)h->R)))
+    if ((rc = encode_2d(&maps[0], h->d_traj, (uint64_t)h->ncols, (uint64_t)h->RD, (uint64_t)h->ldt * 8, xbox,
+                        (uint32_t)h->RD)))
       return rc;
   }
   if (c.tma_store) {
@@ -245,9 +249,15 @@ int launch_eval(opty_colloc* h) {
   p.ldc = h->nn;
   p.n_nodes = h->nn;
   p.n_cols = h->ncols;
+  if (c.num_derived > 0) {
+    void* pargs[1] = {&p};
+    DRV_CHECK(g_drv.LaunchKernel(h->f_pre, (unsigned)((h->nn + 127) / 128), (unsigned)c.pre_groups, 1, 128, 1, 1, 0,
+                                 (CUstream)h->stream, pargs, nullptr));
+    h->launches++;
+  }
   void* args[2] = {h->tmaps[h->ring].data(), &p};
-  DRV_CHECK(g_drv.LaunchKernel(h->f_eval, h->grid_x, (unsigned)c.num_groups, 1, 32u * c.warps_per_block, 1, 1,
-                               h->smem_bytes, (CUstream)h->stream, args, nullptr));
+  DRV_CHECK(g_drv.LaunchKernel(h->f_eval, h->grid_x, (unsigned)c.num_groups, 1, 32u * c.warps_per_block, 1, 1, h->smem_bytes,
+                               (CUstream)h->stream, args, nullptr));
   h->launches++;
   RT_CHECK(cudaEventRecord(h->ev1, h->stream));
   h->have_ms = true;
@@ -301,6 +311,9 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
       cfg->tile_cols > 256)
     return fail(OPTY_ERR_ARG, "invalid kernel geometry");
   if (cfg->out_ring < 1 || cfg->out_ring > 64) return fail(OPTY_ERR_ARG, "invalid out_ring");
+  if (cfg->num_derived < 0 || cfg->pre_groups < 0 || (cfg->num_derived > 0 && cfg->pre_groups < 1) ||
+      cfg->tile_bufs < 2 || cfg->tile_bufs > 4)
+    return fail(OPTY_ERR_ARG, "invalid num_derived / pre_groups / tile_bufs");
   const int expectP = (cfg->method == OPTY_MIDPOINT ? 2 * cfg->n + 2 * cfg->q : 2 * cfg->n + cfg->q) + cfg->r + cfg->s;
   if (cfg->method != OPTY_MIDPOINT && cfg->method != OPTY_BACKWARD_EULER) return fail(OPTY_ERR_ARG, "invalid method");
   if (cfg->P != expectP) return fail(OPTY_ERR_ARG, "P does not match n, q, r, s and the integration method");
@@ -328,10 +341,11 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   h->nn = cfg->node_hi - cfg->node_lo;
   h->ncols = h->nn + 1;
   h->R = cfg->n + cfg->q + cfg->k;
+  h->RD = h->R + cfg->num_derived;
   h->K = cfg->M * cfg->P;
   h->ldt = round_up(h->ncols, 16);
   h->free_len = (size_t)(cfg->n + cfg->q) * cfg->N + cfg->r + cfg->s;
-  if (cfg->tma_load && h->R > 256) {
+  if (cfg->tma_load && h->RD > 256) {
     delete h;
     return fail(OPTY_ERR_ARG, "TMA input staging supports at most 256 trajectory rows");
   }
@@ -354,6 +368,8 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   CREATE_DRV(g_drv.ModuleLoadData(&h->mod, cubin));
   CREATE_DRV(g_drv.ModuleGetFunction(&h->f_eval, h->mod, "opty_colloc_eval"));
   CREATE_DRV(g_drv.ModuleGetFunction(&h->f_inv, h->mod, "opty_colloc_inv"));
+  CREATE_DRV(g_drv.ModuleGetFunction(&h->f_pre, h->mod, "opty_colloc_pre"));
+  CREATE_RT(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   CREATE_DRV(g_drv.ModuleGetGlobal(&h->ci_sym, &h->ci_bytes, h->mod, "opty_ci"));
   if (h->ci_bytes < (size_t)cfg->num_inv * 8) {
     opty_colloc_destroy(h);
@@ -364,8 +380,8 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   CREATE_RT(cudaEventCreate(&h->ev0));
   CREATE_RT(cudaEventCreate(&h->ev1));
 
-  CREATE_RT(cudaMalloc(&h->d_traj, (size_t)h->R * h->ldt * 8));
-  CREATE_RT(cudaMemsetAsync(h->d_traj, 0, (size_t)h->R * h->ldt * 8, h->stream));
+  CREATE_RT(cudaMalloc(&h->d_traj, (size_t)h->RD * h->ldt * 8));
+  CREATE_RT(cudaMemsetAsync(h->d_traj, 0, (size_t)h->RD * h->ldt * 8, h->stream));
   const int nuni = cfg->pk + cfg->r + 1;
   CREATE_RT(cudaMalloc(&h->d_uni, (size_t)nuni * 8));
   CREATE_RT(cudaMemsetAsync(h->d_uni, 0, (size_t)nuni * 8, h->stream));
@@ -392,18 +408,19 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   CREATE_RT(cudaHostAlloc(&h->h_con, ((size_t)cfg->M * h->nn + cfg->con_tail) * 8, cudaHostAllocDefault));
   CREATE_RT(cudaHostAlloc(&h->h_jac, ((size_t)h->nn * h->K + cfg->jac_tail) * 8, cudaHostAllocDefault));
 
-  const unsigned tiles_bytes = (unsigned)cfg->warps_per_block * 2u * 32u * cfg->tile_cols * 8u;
+  const unsigned tiles_bytes = (unsigned)cfg->warps_per_block * (unsigned)cfg->tile_bufs * 32u * cfg->tile_cols * 8u;
   const unsigned threads = 32u * cfg->warps_per_block;
   const unsigned xseg = threads <= 128u ? threads : 128u;
   const unsigned nseg = threads / xseg;
-  const unsigned xin_bytes = nseg * (unsigned)round_up((int64_t)h->R * (xseg + 2u) * 8, 128);
+  const unsigned xin_bytes = nseg * (unsigned)round_up((int64_t)h->RD * (xseg + 2u) * 8, 128);
   h->smem_bytes = tiles_bytes + xin_bytes + 128u;
   if (h->smem_bytes > 227u * 1024u) {
     opty_colloc_destroy(h);
     return fail(OPTY_ERR_ARG, "kernel needs more than 227 KB of shared memory per block");
   }
   CREATE_DRV(g_drv.FuncSetAttribute(h->f_eval, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)h->smem_bytes));
-  h->grid_x = (unsigned)((h->nn + 32 * cfg->warps_per_block - 1) / (32 * cfg->warps_per_block));
+  h->n_tiles = (h->nn + 32 * cfg->warps_per_block - 1) / (32 * cfg->warps_per_block);
+  h->grid_x = (unsigned)h->n_tiles;
   CREATE_RT(cudaStreamSynchronize(h->stream));
   *out = h;
   return OPTY_OK;

@@ -118,23 +118,54 @@ class CollocationProgram(object):
         return out
 
     # ------------------------------------------------------------------
-    def group_nodes(self, rows):
+    def group_nodes(self, rows, stop=None):
         """Node-varying tape ids (topologically sorted) that the outputs of
-        EOM ``rows`` need."""
+        EOM ``rows`` need.  Nodes in ``stop`` (derived rows computed by the
+        pre-pass) are treated as inputs."""
         T = self.tape
         roots = []
         for j in rows:
             roots.append(self.con[j])
             roots.extend(self.jac[j])
-        return [i for i in T.reachable(roots)
-                if T.varying[i] and T.op[i] != ir.VIN]
+        ids = self._reachable_stop(roots, stop) if stop else T.reachable(roots)
+        return [i for i in ids if T.varying[i] and T.op[i] != ir.VIN and
+                not (stop and i in stop)]
+
+    def _reachable_stop(self, roots, stop):
+        T = self.tape
+        seen = set()
+        stack = list(roots)
+        while stack:
+            i = stack.pop()
+            if i in seen:
+                continue
+            seen.add(i)
+            if i in stop:
+                continue
+            stack.extend(T.operands(i))
+        return sorted(seen)
+
+    def select_derived(self, parts, min_cost=12.0, max_rows=128):
+        """Node-varying sub-expressions worth computing once per node in the
+        pre-pass instead of once per output group: expensive operations
+        (transcendentals, divisions, roots: ``OP_COST >= min_cost``) that at
+        least two groups need.  Returns tape ids, most valuable first."""
+        T = self.tape
+        use = {}
+        for r0, r1 in parts:
+            for i in self.group_nodes(range(r0, r1)):
+                if ir.OP_COST[T.op[i]] >= min_cost:
+                    use[i] = use.get(i, 0) + 1
+        cand = [i for i, c in use.items() if c >= 2]
+        cand.sort(key=lambda i: (-(use[i] - 1) * ir.OP_COST[T.op[i]], i))
+        return sorted(cand[:max_rows])
 
     def row_costs(self):
         T = self.tape
         return [T.cost(self.group_nodes([j])) + 2.0 * self.P
                 for j in range(self.M)]
 
-    def partition_rows(self, num_groups, col_align=2):
+    def partition_rows(self, num_groups, col_align=2, stop=None):
         """Splits the EOM rows into at most ``num_groups`` contiguous ranges
         of balanced cost.  Each group's first Jacobian column ``r0*P`` is kept
         a multiple of ``col_align`` (TMA needs 16-byte aligned tile origins).
@@ -154,7 +185,7 @@ class CollocationProgram(object):
             key = (r0, r1)
             c = cost_cache.get(key)
             if c is None:
-                c = (self.tape.cost(self.group_nodes(range(r0, r1))) +
+                c = (self.tape.cost(self.group_nodes(range(r0, r1), stop)) +
                      2.0 * P * (r1 - r0))
                 cost_cache[key] = c
             return c

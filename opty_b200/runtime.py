@@ -13,7 +13,7 @@ import numpy as np
 from . import build
 
 OPTY_MAX_GROUPS = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     'opty_b200_abi_version', 'opty_colloc_create', 'opty_colloc_destroy',
@@ -45,14 +45,16 @@ class ColloCfg(ctypes.Structure):
         ('method', ctypes.c_int32),
         ('num_inv', ctypes.c_int32),
         ('num_groups', ctypes.c_int32),
+        ('num_derived', ctypes.c_int32),
         ('tile_cols', ctypes.c_int32),
         ('warps_per_block', ctypes.c_int32),
+        ('pre_groups', ctypes.c_int32),
+        ('tile_bufs', ctypes.c_int32),
         ('tma_load', ctypes.c_int32),
         ('tma_store', ctypes.c_int32),
         ('out_ring', ctypes.c_int32),
         ('con_tail', ctypes.c_int32),
         ('jac_tail', ctypes.c_int32),
-        ('reserved0', ctypes.c_int32),
         ('group_col0', ctypes.c_int32 * OPTY_MAX_GROUPS),
         ('group_ncols', ctypes.c_int32 * OPTY_MAX_GROUPS),
         ('h', ctypes.c_double),

@@ -34,24 +34,29 @@ def compile_for_host(source):
     return ctypes.CDLL(so)
 
 
+def _prepare_without_nvcc(collocator):
+    """The product's own lowering / grouping / emission
+    (``_PreparedModule``), minus the nvcc step."""
+    from opty_b200 import build
+    from opty_b200.direct_collocation import _PreparedModule
+    real = build.compile_module
+    build.compile_module = lambda *a, **k: (b'', '', False)
+    try:
+        if collocator._cuda_options['groups'] == 'auto':
+            collocator._cuda_options['groups'] = 3
+        pm = _PreparedModule(collocator)
+    finally:
+        build.compile_module = real
+    return pm.program, pm.source, pm.meta
+
+
 def host_evaluate(collocator, free, known_traj=None):
     """Evaluates constraints and Jacobian of ``collocator`` (an
     ``opty_b200.ConstraintCollocator``) at ``free`` with the emitted code
     compiled for the host.  Returns ``(con, jac)`` in the reference layouts
     (eom-major residuals, node-major partials), EOM part only."""
-    from opty_b200 import codegen
-    from opty_b200.program import CollocationProgram
-    rows, uniform, wrt = collocator._program_inputs()
-    opts = collocator._cuda_options
-    prog = CollocationProgram(list(collocator.discrete_eom), rows, uniform,
-                              wrt, use_sympy_cse=opts['use_sympy_cse'])
-    groups = opts['groups']
-    if groups == 'auto':
-        groups = 3
-    parts = prog.partition_rows(int(groups), col_align=2)
-    source, meta = codegen.emit_module(prog, parts,
-                                       collocator.integration_method,
-                                       tile_cols=opts['tile_cols'])
+    prepared = _prepare_without_nvcc(collocator)
+    prog, source, meta = prepared
     lib = compile_for_host(source)
     N = collocator.num_collocation_nodes
     n = collocator.num_states
@@ -59,7 +64,7 @@ def host_evaluate(collocator, free, known_traj=None):
     k = collocator.num_known_input_trajectories
     r = collocator.num_unknown_parameters
     free = np.ascontiguousarray(free, dtype=float)
-    traj = np.zeros((n + q + k, N))
+    traj = np.zeros((n + q + k + meta['D'], N))
     traj[:n + q] = free[:(n + q) * N].reshape(n + q, N)
     for i, sym in enumerate(collocator.known_input_trajectories):
         val = collocator.known_trajectory_map[sym]

@@ -1,9 +1,10 @@
 // TEST INFRASTRUCTURE ONLY -- never used by the product path.
 //
 // Host stand-in for opty_b200/csrc/colloc_kernel.cuh: lets the CPU test-suite
-// compile an emitted module with g++ and run its group bodies node by node, so
-// that the SymPy -> tape -> CUDA-C emitter (lowering, differentiation, chunk /
-// column bookkeeping) can be checked against the oracle without a GPU.
+// compile an emitted module with g++ and run its pre-pass and group bodies
+// node by node, so that the SymPy -> tape -> CUDA-C emitter (lowering,
+// differentiation, derived rows, chunk / column bookkeeping) can be checked
+// against the oracle without a GPU.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -18,7 +19,7 @@
 
 struct OptyTmaps { int unused; };
 struct OptyParams {
-  const double* traj; double* con; double* jac;
+  double* traj; double* con; double* jac;
   long long ldt; long long ldc; int n_nodes; int n_cols;
 };
 struct Dim3 { unsigned x, y, z; };
@@ -29,33 +30,50 @@ static double opty_ci[OPTY_NINV];
 
 struct OptyCtx {
   const double* xs; long long ldt; double* con; long long ldc; double* jac;
-  int node; double tile[2][OPTY_C];
+  int node; double tile[4][OPTY_C];
 };
 
 static inline double opty_sign(double x) { return (double)((x > 0.0) - (x < 0.0)); }
 
 #define XA(r) ctx.xs[(long long)(r) * ctx.ldt]
 #define XB(r) ctx.xs[(long long)(r) * ctx.ldt + 1]
+#define XD(d) ctx.xs[(long long)(OPTY_R + (d)) * ctx.ldt]
 #define OPTY_CON(j, val) ctx.con[(long long)(j) * ctx.ldc] = (val)
 #define OPTY_JS2(buf, tc, v0, v1) do { const_cast<OptyCtx&>(ctx).tile[buf][tc] = (v0); const_cast<OptyCtx&>(ctx).tile[buf][(tc) + 1] = (v1); } while (0)
 #define OPTY_JS1(buf, tc, v0) const_cast<OptyCtx&>(ctx).tile[buf][tc] = (v0)
 #define OPTY_FLUSH(g, q, col0, ncols) \
-  memcpy(ctx.jac + (long long)ctx.node * OPTY_K + (col0) + (q) * OPTY_C, ctx.tile[(q) & 1], (ncols) * sizeof(double))
+  memcpy(ctx.jac + (long long)ctx.node * OPTY_K + (col0) + (q) * OPTY_C, ctx.tile[(q) % OPTY_NBUF], (ncols) * sizeof(double))
 #define OPTY_DRAIN() do { } while (0)
 #define OPTY_THREADS 1
-#define OPTY_PROLOGUE() \
+#define OPTY_PRE_THREADS 1
+#define OPTY_KERNEL_BEGIN() \
   OptyCtx ctx; ctx.node = (int)blockIdx.x; ctx.xs = p.traj + ctx.node; ctx.ldt = p.ldt; \
-  ctx.con = p.con + ctx.node; ctx.ldc = p.ldc; ctx.jac = p.jac; (void)tm;
+  ctx.con = p.con + ctx.node; ctx.ldc = p.ldc; ctx.jac = p.jac; (void)tm; \
+  const int opty_g = opty_group_order[blockIdx.y];
+#define OPTY_KERNEL_END()
+
+#define GA(r) xg[(long long)(r) * p.ldt]
+#define GB(r) xg[(long long)(r) * p.ldt + 1]
+#define OPTY_DRV(d, val) drv[(long long)(d) * p.ldt] = (val)
+#define OPTY_PRE_BEGIN() \
+  const int node = (int)blockIdx.x; \
+  const double* xg = p.traj + node; \
+  double* drv = p.traj + (long long)OPTY_R * p.ldt + node; \
+  const int opty_pg = (int)blockIdx.y;
 
 extern "C" void opty_colloc_inv(const double* uni, double* inv);
+extern "C" void opty_colloc_pre(const OptyParams p);
 extern "C" void opty_colloc_eval(const OptyTmaps tm, const OptyParams p);
 
-extern "C" void host_eval(const double* uni, const double* traj, long long ldt, int n_nodes,
+// traj must have OPTY_R + OPTY_D rows
+extern "C" void host_eval(const double* uni, double* traj, long long ldt, int n_nodes,
                           double* con, double* jac) {
   threadIdx.x = threadIdx.y = 0; blockIdx.x = blockIdx.y = 0;
   opty_colloc_inv(uni, opty_ci);
   OptyTmaps tm; OptyParams p;
   p.traj = traj; p.con = con; p.jac = jac; p.ldt = ldt; p.ldc = n_nodes; p.n_nodes = n_nodes; p.n_cols = n_nodes + 1;
+  for (int pg = 0; pg < 64; ++pg)
+    for (int i = 0; i < n_nodes; ++i) { blockIdx.x = i; blockIdx.y = pg; opty_colloc_pre(p); }
   for (int g = 0; g < OPTY_NGROUPS; ++g)
     for (int i = 0; i < n_nodes; ++i) { blockIdx.x = i; blockIdx.y = g; opty_colloc_eval(tm, p); }
 }

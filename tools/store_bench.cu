@@ -64,6 +64,23 @@ __global__ void __launch_bounds__(256) store_kernel(const __grid_constant__ CUte
       }
       continue;
     }
+    if (MODE == 7) {
+      // tile rows padded by one 16-byte vector: pitch (C + 2) doubles
+      const int pitch = C + 2;
+      double* t7 = reinterpret_cast<double*>(smem + (size_t)warp * 32 * pitch * 8);
+      for (int c = 0; c + 1 < ncols; c += 2)
+        *reinterpret_cast<double2*>(t7 + lane * pitch + c) = make_double2(v, v + c);
+      __syncwarp();
+      const int V = ncols >> 1;          // 16-byte vectors per row
+      const int rows = min(32, nodes - node0);
+      for (int idx = lane; idx < rows * V; idx += 32) {
+        const int r = idx / V, vv = idx - r * V;
+        *reinterpret_cast<double2*>(out + (long long)(node0 + r) * Kp + q * C + 2 * vv) =
+            *reinterpret_cast<const double2*>(t7 + r * pitch + 2 * vv);
+      }
+      __syncwarp();
+      continue;
+    }
     unsigned char* tile = mytiles + (q % nbuf) * tile_bytes;
     for (int c = 0; c + 1 < ncols; c += 2) {
       int chunk16 = c >> 1;
@@ -81,8 +98,9 @@ __global__ void __launch_bounds__(256) store_kernel(const __grid_constant__ CUte
       __syncwarp();
       continue;
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (MODE != 5) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
+    if (MODE == 6) continue;
     if (lane == 0) {
       tma_store_2d(&tm, tile, q * C, node0);
       if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -92,7 +110,7 @@ __global__ void __launch_bounds__(256) store_kernel(const __grid_constant__ CUte
     }
     __syncwarp();
   }
-  if (MODE < 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if ((MODE < 2 || MODE == 5) && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 struct Variant {
@@ -115,39 +133,22 @@ int main() {
   CK(cudaEventCreate(&e1));
 
   std::vector<Variant> vs = {
-      {"tma dense  K1012 p1012 C30 W2 nb2", 0, 1012, 1012, 30, 2, 2, 0, 1},
-      {"tma dense  K1012 p1012 C14 W2 nb2", 0, 1012, 1012, 14, 2, 2, 0, 1},
-      {"tma dense  K1012 p1012 C30 W8 nb2", 0, 1012, 1012, 30, 8, 2, 0, 1},
-      {"tma dense  K1012 p1012 C62 W2 nb2", 0, 1012, 1012, 62, 2, 2, 0, 1},
-      {"tma dense  K1012 p1012 C126 W2 nb2", 0, 1012, 1012, 126, 2, 2, 0, 1},
-      {"tma dense  K1012 p1012 C30 W2 nb4", 0, 1012, 1012, 30, 2, 4, 0, 1},
-      {"tma dense  K1012 p1024 C30 W2 nb2", 0, 1012, 1024, 30, 2, 2, 0, 1},
-      {"tma dense  K1012 p1024 C16 W2 nb2", 0, 1012, 1024, 16, 2, 2, 0, 1},
-      {"tma swz128 K1012 p1024 C16 W2 nb2", 1, 1012, 1024, 16, 2, 2, 0, 1},
-      {"tma swz128 K1012 p1024 C16 W8 nb2", 1, 1012, 1024, 16, 8, 2, 0, 1},
-      {"tma swz128 K1012 p1024 C16 W8 nb4", 1, 1012, 1024, 16, 8, 4, 0, 1},
-      {"tma swz128 K1012 p1012 C16 W2 nb2", 1, 1012, 1012, 16, 2, 2, 0, 1},
-      {"tma dense  K1012 p1024 C32 W2 nb2", 0, 1012, 1024, 32, 2, 2, 0, 1},
-      {"tma dense  K1012 p1024 C64 W2 nb2", 0, 1012, 1024, 64, 2, 2, 0, 1},
-      {"tma dense  K1012 p1024 C128 W2 nb2", 0, 1012, 1024, 128, 2, 2, 0, 1},
-      {"direct v2  K1012 p1012 W2", 2, 1012, 1012, 30, 2, 2, 0, 1},
-      {"warp-row   K1012 p1012 C30 W2", 3, 1012, 1012, 30, 2, 2, 0, 1},
-      {"warp-row   K1012 p1024 C64 W2", 3, 1012, 1024, 64, 2, 2, 0, 1},
-      {"tma dense  K1012 p1012 C30 W2 nb2 G4", 0, 1012, 1012, 30, 2, 2, 0, 4},
-      {"tma dense  K1012 p1012 C30 W2 nb2 G8", 0, 1012, 1012, 30, 2, 2, 0, 8},
-      {"tma dense  K1012 p1012 C30 W2 nb2 G16", 0, 1012, 1012, 30, 2, 2, 0, 16},
-      {"tma dense  K1012 p1012 C62 W2 nb2 G8", 0, 1012, 1012, 62, 2, 2, 0, 8},
-      {"tma dense  K1012 p1012 C126 W2 nb2 G8", 0, 1012, 1012, 126, 2, 2, 0, 8},
-      {"tma dense  K1012 p1012 C14 W2 nb2 G8", 0, 1012, 1012, 14, 2, 2, 0, 8},
-      {"tma swz128 K1012 p1024 C16 W2 nb2 G8", 1, 1012, 1024, 16, 2, 2, 0, 8},
-      {"tma swz128 K1012 p1012 C16 W2 nb2 G8", 1, 1012, 1012, 16, 2, 2, 0, 8},
-      {"tma dense  K1012 p1012 C30 W8 nb2 G8", 0, 1012, 1012, 30, 8, 2, 0, 8},
-      {"direct v2  K1012 p1012 W2 G8", 2, 1012, 1012, 30, 2, 2, 0, 8},
-      {"warp-row   K1012 p1012 C30 W2 G8", 3, 1012, 1012, 30, 2, 2, 0, 8},
-      {"tma dense  K1012 p1012 C30 W2 nb2 G8 work40", 0, 1012, 1012, 30, 2, 2, 40, 8},
-      {"tma dense  K1012 p1012 C30 W2 nb2 work40", 0, 1012, 1012, 30, 2, 2, 40, 1},
-      {"tma swz128 K1012 p1024 C16 W2 nb2 work40", 1, 1012, 1024, 16, 2, 2, 40, 1},
+      {"tma   store only          C30 G8", 0, 1012, 1012, 30, 2, 2, 0, 8},
+      {"lsu16 store only          C30 G8", 7, 1012, 1012, 30, 2, 1, 0, 8},
+      {"lsu16 store only          C62 G8", 7, 1012, 1012, 62, 2, 1, 0, 8},
+      {"lsu16 store only          C64 G8", 7, 1012, 1012, 64, 2, 1, 0, 8},
+      {"lsu16 store only          C128 G8", 7, 1012, 1012, 128, 2, 1, 0, 8},
+      {"lsu16 store only          C46 G11", 7, 1012, 1012, 46, 2, 1, 0, 11},
+      {"lsu16 store only  W4      C62 G8", 7, 1012, 1012, 62, 4, 1, 0, 8},
+      {"compute only w1000        C30 G8", 6, 1012, 1012, 30, 2, 2, 1000, 8},
+      {"tma   store+compute w1000 C30 G8", 0, 1012, 1012, 30, 2, 2, 1000, 8},
+      {"lsu16 store+compute w1000 C30 G8", 7, 1012, 1012, 30, 2, 1, 1000, 8},
+      {"lsu16 store+compute w1000 C62 G8", 7, 1012, 1012, 62, 2, 1, 2000, 8},
+      {"lsu16 store+compute w500  C30 G8", 7, 1012, 1012, 30, 2, 1, 500, 8},
+      {"tma   store+compute w500  C30 G8", 0, 1012, 1012, 30, 2, 2, 500, 8},
   };
+
+
 
   for (const Variant& v : vs) {
     std::vector<CUtensorMap> maps(nring);
@@ -170,7 +171,7 @@ int main() {
     if (!ok) continue;
     const int threads = v.warps * 32;
     const int blocks = (nodes + threads - 1) / threads;
-    const size_t smem = (size_t)v.warps * v.nbuf * 32 * v.C * 8 + 1024;
+    const size_t smem = (size_t)v.warps * v.nbuf * 32 * (v.C + 2) * 8 + 1024;
     auto launch = [&](int r) {
       switch (v.mode) {
         case 0:
@@ -183,6 +184,18 @@ int main() {
           break;
         case 2:
           store_kernel<2><<<dim3(blocks, v.G), threads, smem, st>>>(maps[r], bufs[r], nodes, v.K, v.Kp, v.C, v.nbuf, v.work, v.G);
+          break;
+        case 5:
+          cudaFuncSetAttribute(store_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          store_kernel<5><<<dim3(blocks, v.G), threads, smem, st>>>(maps[r], bufs[r], nodes, v.K, v.Kp, v.C, v.nbuf, v.work, v.G);
+          break;
+        case 7:
+          cudaFuncSetAttribute(store_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          store_kernel<7><<<dim3(blocks, v.G), threads, smem, st>>>(maps[r], bufs[r], nodes, v.K, v.Kp, v.C, v.nbuf, v.work, v.G);
+          break;
+        case 6:
+          cudaFuncSetAttribute(store_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          store_kernel<6><<<dim3(blocks, v.G), threads, smem, st>>>(maps[r], bufs[r], nodes, v.K, v.Kp, v.C, v.nbuf, v.work, v.G);
           break;
         default:
           cudaFuncSetAttribute(store_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
