@@ -43,7 +43,11 @@ extern "C" {
 #define OPTY_ERR_CUDA -2    /* CUDA runtime or driver error */
 #define OPTY_ERR_STATE -3   /* call sequence error (e.g. known values not set) */
 
-enum { OPTY_BACKWARD_EULER = 0, OPTY_MIDPOINT = 1 };
+/* OPTY_ELEMENTWISE: the generic `ufuncify_matrix` operator (opty/utils.py:
+ * 639-670): N evaluation points, n array arguments of length N, r scalar
+ * ("const") arguments after them in `free`, an M x P output matrix per point
+ * (returned through opty_colloc_jacobian), no residuals, no neighbour column. */
+enum { OPTY_BACKWARD_EULER = 0, OPTY_MIDPOINT = 1, OPTY_ELEMENTWISE = 2 };
 
 /* Problem + kernel geometry.  Symbols follow the reference's notation
  * (opty/direct_collocation.py:101-114). */

@@ -283,8 +283,10 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 g, chunk, col0, ncols_in_chunk))
 
         for j in range(r0, r1):
-            bw.need(prog.con[j])
-            body.append('OPTY_CON({}, {});'.format(j, bw.ref(prog.con[j])))
+            if prog.con:
+                bw.need(prog.con[j])
+                body.append('OPTY_CON({}, {});'.format(
+                    j, bw.ref(prog.con[j])))
             for k in range(P):
                 e = prog.jac[j][k]
                 bw.need(e)

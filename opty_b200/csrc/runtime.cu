@@ -300,10 +300,11 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   if (!cfg || !cubin || !out || cubin_bytes == 0) return fail(OPTY_ERR_ARG, "null argument");
   *out = nullptr;
   if (cfg->abi_version != OPTY_B200_ABI_VERSION) return fail(OPTY_ERR_ARG, "ABI version mismatch");
-  if (cfg->N < 2 || cfg->n < 1 || cfg->M < 1 || cfg->P < 1 || cfg->q < 0 || cfg->k < 0 || cfg->r < 0 ||
+  if (cfg->N < (cfg->method == OPTY_ELEMENTWISE ? 1 : 2) || cfg->n < (cfg->method == OPTY_ELEMENTWISE ? 0 : 1) || cfg->M < 1 || cfg->P < 1 || cfg->q < 0 || cfg->k < 0 || cfg->r < 0 ||
       cfg->pk < 0 || (cfg->s != 0 && cfg->s != 1))
     return fail(OPTY_ERR_ARG, "invalid problem dimensions");
-  if (cfg->node_lo < 0 || cfg->node_hi > cfg->N - 1 || cfg->node_lo >= cfg->node_hi)
+  const bool elementwise = cfg->method == OPTY_ELEMENTWISE;
+  if (cfg->node_lo < 0 || cfg->node_hi > cfg->N - (elementwise ? 0 : 1) || cfg->node_lo >= cfg->node_hi)
     return fail(OPTY_ERR_ARG, "invalid node range");
   if (cfg->num_groups < 1 || cfg->num_groups > OPTY_MAX_GROUPS) return fail(OPTY_ERR_ARG, "invalid group count");
   if (cfg->warps_per_block < 1 || cfg->warps_per_block > 32 ||
@@ -315,8 +316,10 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
       cfg->tile_bufs < 2 || cfg->tile_bufs > 4)
     return fail(OPTY_ERR_ARG, "invalid num_derived / pre_groups / tile_bufs");
   const int expectP = (cfg->method == OPTY_MIDPOINT ? 2 * cfg->n + 2 * cfg->q : 2 * cfg->n + cfg->q) + cfg->r + cfg->s;
-  if (cfg->method != OPTY_MIDPOINT && cfg->method != OPTY_BACKWARD_EULER) return fail(OPTY_ERR_ARG, "invalid method");
-  if (cfg->P != expectP) return fail(OPTY_ERR_ARG, "P does not match n, q, r, s and the integration method");
+  if (cfg->method != OPTY_MIDPOINT && cfg->method != OPTY_BACKWARD_EULER && !elementwise)
+    return fail(OPTY_ERR_ARG, "invalid method");
+  if (!elementwise && cfg->P != expectP)
+    return fail(OPTY_ERR_ARG, "P does not match n, q, r, s and the integration method");
   {
     long long covered = 0;
     for (int g = 0; g < cfg->num_groups; ++g) {
@@ -339,7 +342,7 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   opty_colloc* h = new opty_colloc();
   h->cfg = *cfg;
   h->nn = cfg->node_hi - cfg->node_lo;
-  h->ncols = h->nn + 1;
+  h->ncols = h->nn + (elementwise ? 0 : 1);
   h->R = cfg->n + cfg->q + cfg->k;
   h->RD = h->R + cfg->num_derived;
   h->K = cfg->M * cfg->P;

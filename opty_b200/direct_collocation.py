@@ -528,6 +528,72 @@ class ConstraintCollocator(object):
         return self._node_range == (0, self._num_collocation_nodes - 1)
 
 
+def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
+                           show_compile_output=False):
+    """Groups, emits and compiles the CUDA module of a
+    :class:`CollocationProgram` for ``num_nodes`` evaluation nodes.  Needs nvcc
+    but no GPU.  Returns ``(parts, derived, source, meta, cubin, cubin_path,
+    cache_hit)``."""
+    M = prog.M
+    K = M * prog.P
+    tma_store = bool(opts['tma_store']) and K % 2 == 0
+    tma_load = bool(opts['tma_load']) and prog.R <= 256
+    groups = opts['groups']
+    if groups == 'auto':
+        node_warps = -(-num_nodes // 32)
+        g_par = -(-int(opts['target_warps']) // node_warps)
+        g_cost = int(np.ceil(prog.stats()['varying_cost'] /
+                             float(opts['max_group_cost'])))
+        groups = max(1, g_par, g_cost)
+    groups = int(min(groups, M, runtime.OPTY_MAX_GROUPS))
+    align = 2 if tma_store else 1
+    parts = prog.partition_rows(groups, col_align=align)
+    derived = []
+    if opts['pre_pass'] and len(parts) > 1:
+        derived = prog.select_derived(parts, max_rows=max(0, 256 - prog.R))
+        if derived:
+            # re-balance with the shared work taken out of the groups
+            parts = prog.partition_rows(groups, col_align=align,
+                                        stop=set(derived))
+    if prog.R + len(derived) > 256:
+        tma_load = False
+
+    logger.info('Emitting the CUDA module.')
+    source, meta = codegen.emit_module(
+        prog, parts, method,
+        tile_cols=opts['tile_cols'],
+        warps_per_block=opts['warps_per_block'],
+        min_blocks_per_sm=opts['min_blocks_per_sm'],
+        tma_load=tma_load, tma_store=tma_store, derived=derived,
+        debug_nostore=opts['debug_nostore'],
+        tile_bufs=opts['tile_bufs'])
+    flags = build.module_flags(fmad=opts['fmad'],
+                               maxrregcount=opts['maxrregcount'])
+    logger.info('Compiling the constraint and Jacobian kernels.')
+    cubin, cubin_path, cache_hit = build.compile_module(
+        source, flags, cache_dir=tmp_dir,
+        show_compile_output=show_compile_output)
+    return parts, derived, source, meta, cubin, cubin_path, cache_hit
+
+
+def fill_kernel_config(cfg, meta, opts):
+    """Copies the kernel geometry of an emitted module into a ``ColloCfg``."""
+    cfg.abi_version = runtime.ABI_VERSION
+    cfg.num_inv = meta['num_inv']
+    cfg.num_groups = meta['num_groups']
+    cfg.num_derived = meta['D']
+    cfg.tile_cols = meta['C']
+    cfg.warps_per_block = meta['warps_per_block']
+    cfg.pre_groups = meta['pre_groups']
+    cfg.tile_bufs = meta['tile_bufs']
+    cfg.tma_load = int(meta['tma_load'])
+    cfg.tma_store = int(meta['tma_store'])
+    cfg.out_ring = int(opts['out_ring'])
+    for g, gm in enumerate(meta['groups']):
+        cfg.group_col0[g] = gm['col0']
+        cfg.group_ncols[g] = gm['ncols']
+
+
 class _PreparedModule(object):
     """Tape program, emitted CUDA-C and compiled cubin of one collocator.
     Building it needs nvcc but no GPU (``__graft_entry__.build`` uses this to
@@ -541,47 +607,9 @@ class _PreparedModule(object):
                                   use_sympy_cse=opts['use_sympy_cse'])
         self.program = prog
         lo, hi = col._node_range
-        nn = hi - lo
-        M = prog.M
-        K = M * prog.P
-
-        tma_store = bool(opts['tma_store']) and K % 2 == 0
-        tma_load = bool(opts['tma_load']) and prog.R <= 256
-        groups = opts['groups']
-        if groups == 'auto':
-            node_warps = -(-nn // 32)
-            g_par = -(-int(opts['target_warps']) // node_warps)
-            g_cost = int(np.ceil(prog.stats()['varying_cost'] /
-                                 float(opts['max_group_cost'])))
-            groups = max(1, g_par, g_cost)
-        groups = int(min(groups, M, runtime.OPTY_MAX_GROUPS))
-        align = 2 if tma_store else 1
-        self.parts = prog.partition_rows(groups, col_align=align)
-        self.derived = []
-        if opts['pre_pass'] and len(self.parts) > 1:
-            self.derived = prog.select_derived(
-                self.parts, max_rows=max(0, 256 - prog.R))
-            if self.derived:
-                # re-balance with the shared work taken out of the groups
-                self.parts = prog.partition_rows(
-                    groups, col_align=align, stop=set(self.derived))
-        if prog.R + len(self.derived) > 256:
-            tma_load = False
-
-        logger.info('Emitting the CUDA module.')
-        self.source, self.meta = codegen.emit_module(
-            prog, self.parts, col.integration_method,
-            tile_cols=opts['tile_cols'],
-            warps_per_block=opts['warps_per_block'],
-            min_blocks_per_sm=opts['min_blocks_per_sm'],
-            tma_load=tma_load, tma_store=tma_store, derived=self.derived,
-            debug_nostore=opts['debug_nostore'],
-            tile_bufs=opts['tile_bufs'])
-        flags = build.module_flags(fmad=opts['fmad'],
-                                   maxrregcount=opts['maxrregcount'])
-        logger.info('Compiling the constraint and Jacobian kernels.')
-        self.cubin, self.cubin_path, self.cache_hit = build.compile_module(
-            self.source, flags, cache_dir=col.tmp_dir,
+        (self.parts, self.derived, self.source, self.meta, self.cubin,
+         self.cubin_path, self.cache_hit) = prepare_program_module(
+            prog, hi - lo, col.integration_method, opts, tmp_dir=col.tmp_dir,
             show_compile_output=col.show_compile_output)
 
 
@@ -614,7 +642,7 @@ class _CudaEvaluator(object):
         self.nnz_inst = nnz_inst
 
         cfg = runtime.ColloCfg()
-        cfg.abi_version = runtime.ABI_VERSION
+        fill_kernel_config(cfg, meta, opts)
         cfg.device = col._device
         cfg.N = col.num_collocation_nodes
         cfg.node_lo, cfg.node_hi = lo, hi
@@ -626,21 +654,8 @@ class _CudaEvaluator(object):
         cfg.pk = col.num_known_parameters
         cfg.M, cfg.P = M, P
         cfg.method = 1 if col.integration_method == 'midpoint' else 0
-        cfg.num_inv = meta['num_inv']
-        cfg.num_groups = meta['num_groups']
-        cfg.num_derived = meta['D']
-        cfg.tile_cols = meta['C']
-        cfg.warps_per_block = meta['warps_per_block']
-        cfg.pre_groups = meta['pre_groups']
-        cfg.tile_bufs = meta['tile_bufs']
-        cfg.tma_load = int(meta['tma_load'])
-        cfg.tma_store = int(meta['tma_store'])
-        cfg.out_ring = int(opts['out_ring'])
         cfg.con_tail = o
         cfg.jac_tail = nnz_inst
-        for g, gm in enumerate(meta['groups']):
-            cfg.group_col0[g] = gm['col0']
-            cfg.group_ncols[g] = gm['ncols']
         cfg.h = 0.0 if col._variable_duration else float(
             col.node_time_interval)
         self.handle = runtime.ColloHandle(cfg, cubin)

@@ -40,6 +40,50 @@ class CollocationProgram(object):
         (opty/direct_collocation.py:2719-2721, 2734-2737).
     """
 
+    @classmethod
+    def from_matrix(cls, args, expr, const=(), use_sympy_cse=True):
+        """Program that evaluates a matrix of expressions element-wise over
+        arrays: the generic operator of ``ufuncify_matrix`` (opty/utils.py:
+        639-670).  Non-``const`` args become rows of the trajectory matrix,
+        ``const`` args uniform inputs; the ``rows x cols`` matrix entries take
+        the place of the Jacobian block and there are no residual outputs.
+
+        ``expr`` is a SymPy matrix or the ``(replacements, [matrix])`` pair
+        that ``sm.cse`` returns."""
+        from .lowering import Lowerer
+        self = cls.__new__(cls)
+        const = tuple(const)
+        T = ir.Tape()
+        leaf = {}
+        row = 0
+        uni = 0
+        for a in args:
+            if a in const:
+                leaf[a] = T.uin(uni)
+                uni += 1
+            else:
+                leaf[a] = T.vin(2 * row)
+                row += 1
+        self.tape = T
+        self.R = row
+        self.num_uniform = uni
+        if isinstance(expr, tuple) and len(expr) == 2:
+            repl, (mat,) = expr
+            low = Lowerer(T, leaf)
+            for sym, sub in repl:
+                low.bind(sym, low.lower(sub))
+            ids = [low.lower(e) for e in mat]
+        else:
+            mat = expr
+            ids = lower_matrix(T, leaf, list(mat), use_sympy_cse=use_sympy_cse)
+        rows, cols = mat.shape
+        self.M, self.P = rows, cols
+        self.K = rows * cols
+        self.con = []
+        self.jac = [ids[j * cols:(j + 1) * cols] for j in range(rows)]
+        self._classify()
+        return self
+
     def __init__(self, discrete_eom, traj_symbols, uniform_symbols, wrt,
                  use_sympy_cse=True):
         self.M = len(discrete_eom)
@@ -125,7 +169,8 @@ class CollocationProgram(object):
         T = self.tape
         roots = []
         for j in rows:
-            roots.append(self.con[j])
+            if self.con:
+                roots.append(self.con[j])
             roots.extend(self.jac[j])
         ids = self._reachable_stop(roots, stop) if stop else T.reachable(roots)
         return [i for i in ids if T.varying[i] and T.op[i] != ir.VIN and

@@ -6,7 +6,7 @@ Same names and call signatures as the corresponding functions of
 
 import numpy as np
 
-__all__ = ['parse_free', 'sort_sympy']
+__all__ = ['parse_free', 'sort_sympy', 'ufuncify_matrix']
 
 
 def parse_free(free, n, q, N, variable_duration=False):
@@ -66,3 +66,12 @@ def _coo_matrix(jac_vals, row_idxs, col_idxs):
     # np's fancy assignment keeps the last value for repeated indices
     dense[np.asarray(row_idxs), np.asarray(col_idxs)] = jac_vals
     return dense
+
+
+def ufuncify_matrix(args, expr, const=None, tmp_dir=None, parallel=False,
+                    show_compile_output=False, **kwargs):
+    """CUDA version of ``opty.utils.ufuncify_matrix`` (opty/utils.py:639-670);
+    see :mod:`opty_b200.ufuncify`."""
+    from .ufuncify import ufuncify_matrix as _impl
+    return _impl(args, expr, const=const, tmp_dir=tmp_dir, parallel=parallel,
+                 show_compile_output=show_compile_output, **kwargs)
