@@ -78,6 +78,7 @@ typedef struct opty_colloc_cfg {
   int32_t out_ring;         /* number of device output sets to rotate (>=1) */
   int32_t con_tail;         /* extra host slots after the M*(N-1) residuals */
   int32_t jac_tail;         /* extra host slots after the (N-1)*M*P partials */
+  int32_t prefetch_jac;     /* opty_colloc_constraints starts the Jacobian D2H speculatively */
   int32_t group_col0[OPTY_MAX_GROUPS];   /* first Jacobian column of group g */
   int32_t group_ncols[OPTY_MAX_GROUPS];  /* number of columns of group g */
   double h;                 /* fixed node time interval (ignored when s=1) */

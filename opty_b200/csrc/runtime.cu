@@ -161,7 +161,10 @@ struct opty_colloc {
   size_t ci_bytes = 0;
 
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // speculative Jacobian D2H
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_con = nullptr;
+  bool jac_inflight = false;
 
   double* d_traj = nullptr;
   double* d_uni = nullptr;
@@ -171,16 +174,19 @@ struct opty_colloc {
   int ring = -1;
 
   double* h_free = nullptr;    // pinned staging copy of the free vector
-  double* h_shadow = nullptr;  // pageable copy used to detect an unchanged vector
   double* h_con = nullptr;
-  double* h_jac = nullptr;
+  double* h_jacs[2] = {nullptr, nullptr};  // [1] only with prefetch_jac: speculative copies never touch the
+                                            // buffer the caller may still be reading
+  double* h_jac = nullptr;                 // buffer holding the most recently fetched Jacobian
+  int jac_cur = 0;                         // its index
+  int jac_target = 0;                      // destination of the copy in flight
+  bool full_fetch[2] = {true, true};       // constant Jacobian columns not yet in that host buffer
 
   bool known_set = false;
   bool free_valid = false;
   bool inv_dirty = true;
   bool evaluated = false;
   bool con_fetched = false, jac_fetched = false;
-  bool full_fetch_needed = true;  // constant Jacobian columns not yet on the host
 
   std::vector<int32_t> d2h_begin, d2h_end;
   unsigned smem_bytes = 0;
@@ -231,6 +237,12 @@ int launch_eval(opty_colloc* h) {
   const opty_colloc_cfg& c = h->cfg;
   if (!h->known_set) return fail(OPTY_ERR_STATE, "opty_colloc_set_known must be called before evaluating");
   if (!h->free_valid) return fail(OPTY_ERR_STATE, "no free vector resident on the device");
+  if (h->jac_inflight) {
+    // a speculative Jacobian copy of the previous evaluation is still running:
+    // order the new kernels (and later copies into the pinned buffer) after it
+    RT_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+    h->jac_inflight = false;
+  }
   RT_CHECK(cudaEventRecord(h->ev0, h->stream));
   if (h->inv_dirty && c.num_inv > 0) {
     void* args[2] = {&h->d_uni, &h->d_inv};
@@ -266,13 +278,51 @@ int launch_eval(opty_colloc* h) {
   return OPTY_OK;
 }
 
+int ensure_host_jac(opty_colloc* h) {
+  const size_t bytes = ((size_t)h->nn * h->K + h->cfg.jac_tail) * 8;
+  if (!h->h_jacs[0]) {
+    RT_CHECK(cudaHostAlloc(&h->h_jacs[0], bytes, cudaHostAllocDefault));
+    h->h_jac = h->h_jacs[0];
+    h->full_fetch[0] = true;
+  }
+  if (h->cfg.prefetch_jac && !h->h_jacs[1]) {
+    RT_CHECK(cudaHostAlloc(&h->h_jacs[1], bytes, cudaHostAllocDefault));
+    h->full_fetch[1] = true;
+  }
+  return OPTY_OK;
+}
+
+int enqueue_jac_copy(opty_colloc* h, cudaStream_t st) {
+  int rc0 = ensure_host_jac(h);
+  if (rc0) return rc0;
+  const size_t bytes = (size_t)h->nn * h->K * 8;
+  const int which = h->h_jacs[1] ? (h->jac_cur ^ 1) : 0;
+  double* dst = h->h_jacs[which];
+  h->jac_target = which;
+  if (h->d2h_begin.empty() || h->full_fetch[which]) {
+    // first fetch into this buffer (and every fetch without column ranges):
+    // the whole block, which also brings the constant columns to the host once
+    RT_CHECK(cudaMemcpyAsync(dst, h->d_jac[h->ring], bytes, cudaMemcpyDeviceToHost, st));
+    h->full_fetch[which] = false;
+  } else {
+    for (size_t i = 0; i < h->d2h_begin.size(); ++i) {
+      const int b = h->d2h_begin[i], e = h->d2h_end[i];
+      RT_CHECK(cudaMemcpy2DAsync(dst + b, (size_t)h->K * 8, h->d_jac[h->ring] + b, (size_t)h->K * 8,
+                                 (size_t)(e - b) * 8, h->nn, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  return OPTY_OK;
+}
+
 int upload(opty_colloc* h, const double* free_host, bool* changed_out) {
   const opty_colloc_cfg& c = h->cfg;
   const size_t bytes = h->free_len * 8;
-  bool changed = !h->free_valid || memcmp(free_host, h->h_shadow, bytes) != 0;
+  // IPOPT evaluates g and jac_g at the same point back to back: compare with
+  // the staged copy (a vector handed over in the pinned buffer itself cannot
+  // be compared and always counts as new)
+  const bool changed = !h->free_valid || free_host == h->h_free || memcmp(free_host, h->h_free, bytes) != 0;
   if (changed_out) *changed_out = changed;
   if (!changed) return OPTY_OK;
-  memcpy(h->h_shadow, free_host, bytes);
   if (free_host != h->h_free) memcpy(h->h_free, free_host, bytes);
   const int rows = c.n + c.q;
   // rows of the free vector are [row][N]; this handle keeps columns node_lo..node_hi
@@ -380,8 +430,11 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   }
 
   CREATE_RT(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_RT(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CREATE_RT(cudaEventCreate(&h->ev0));
   CREATE_RT(cudaEventCreate(&h->ev1));
+  CREATE_RT(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  CREATE_RT(cudaEventCreateWithFlags(&h->ev_con, cudaEventDisableTiming));
 
   CREATE_RT(cudaMalloc(&h->d_traj, (size_t)h->RD * h->ldt * 8));
   CREATE_RT(cudaMemsetAsync(h->d_traj, 0, (size_t)h->RD * h->ldt * 8, h->stream));
@@ -403,13 +456,9 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   }
 
   CREATE_RT(cudaHostAlloc(&h->h_free, h->free_len * 8, cudaHostAllocDefault));
-  h->h_shadow = static_cast<double*>(malloc(h->free_len * 8));
-  if (!h->h_shadow) {
-    opty_colloc_destroy(h);
-    return fail(OPTY_ERR_ARG, "out of host memory");
-  }
   CREATE_RT(cudaHostAlloc(&h->h_con, ((size_t)cfg->M * h->nn + cfg->con_tail) * 8, cudaHostAllocDefault));
-  CREATE_RT(cudaHostAlloc(&h->h_jac, ((size_t)h->nn * h->K + cfg->jac_tail) * 8, cudaHostAllocDefault));
+  // the pinned Jacobian buffers (8.4 GB each at BASELINE config 5) are allocated on first use:
+  // device-resident consumers never need them
 
   const unsigned tiles_bytes = (unsigned)cfg->warps_per_block * (unsigned)cfg->tile_bufs * 32u * cfg->tile_cols * 8u;
   const unsigned threads = 32u * cfg->warps_per_block;
@@ -433,6 +482,7 @@ int opty_colloc_destroy(opty_colloc_t* h) {
   if (!h) return OPTY_OK;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   for (double* p : h->d_con) cudaFree(p);
   for (double* p : h->d_jac) cudaFree(p);
   cudaFree(h->d_traj);
@@ -440,10 +490,13 @@ int opty_colloc_destroy(opty_colloc_t* h) {
   cudaFree(h->d_inv);
   if (h->h_free) cudaFreeHost(h->h_free);
   if (h->h_con) cudaFreeHost(h->h_con);
-  if (h->h_jac) cudaFreeHost(h->h_jac);
-  free(h->h_shadow);
+  if (h->h_jacs[0]) cudaFreeHost(h->h_jacs[0]);
+  if (h->h_jacs[1]) cudaFreeHost(h->h_jacs[1]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->ev_con) cudaEventDestroy(h->ev_con);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(h->mod);
   delete h;
@@ -466,7 +519,7 @@ int opty_colloc_set_known(opty_colloc_t* h, const double* traj, const double* pa
   h->known_set = true;
   h->inv_dirty = true;
   h->evaluated = false;
-  h->full_fetch_needed = true;
+  h->full_fetch[0] = h->full_fetch[1] = true;
   return OPTY_OK;
 }
 
@@ -493,10 +546,28 @@ int opty_colloc_constraints(opty_colloc_t* h, const double* free_host, double* c
   RT_CHECK(cudaSetDevice(h->cfg.device));
   int rc = upload(h, free_host, nullptr);
   if (rc) return rc;
-  if (!h->evaluated && (rc = launch_eval(h))) return rc;
+  bool launched = false;
+  if (!h->evaluated) {
+    if ((rc = launch_eval(h))) return rc;
+    launched = true;
+  }
   const size_t bytes = (size_t)h->cfg.M * h->nn * 8;
   if (!h->con_fetched) {
     RT_CHECK(cudaMemcpyAsync(h->h_con, h->d_con[h->ring], bytes, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (launched && h->cfg.prefetch_jac) {
+    // IPOPT asks for the Jacobian at the point it just evaluated g at: start
+    // moving it now, on a second stream, behind the kernels and the residuals,
+    // into the host buffer the caller is not looking at
+    // (ordered behind the small residual copy: both go through the same
+    // device-to-host copy engine, which would otherwise serve the big one first)
+    RT_CHECK(cudaEventRecord(h->ev_con, h->stream));
+    RT_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_con, 0));
+    if ((rc = enqueue_jac_copy(h, h->copy_stream))) return rc;
+    RT_CHECK(cudaEventRecord(h->ev_copy, h->copy_stream));
+    h->jac_inflight = true;
+  }
+  if (!h->con_fetched) {
     RT_CHECK(cudaStreamSynchronize(h->stream));
     h->con_fetched = true;
   }
@@ -512,19 +583,15 @@ int opty_colloc_jacobian(opty_colloc_t* h, const double* free_host, double* jac_
   if (!h->evaluated && (rc = launch_eval(h))) return rc;
   const size_t bytes = (size_t)h->nn * h->K * 8;
   if (!h->jac_fetched) {
-    if (h->d2h_begin.empty() || h->full_fetch_needed) {
-      // first fetch (and every fetch without column ranges): the whole block,
-      // which also brings the constant columns to the host once
-      RT_CHECK(cudaMemcpyAsync(h->h_jac, h->d_jac[h->ring], bytes, cudaMemcpyDeviceToHost, h->stream));
-      h->full_fetch_needed = false;
+    if (h->jac_inflight) {
+      RT_CHECK(cudaEventSynchronize(h->ev_copy));
+      h->jac_inflight = false;
     } else {
-      for (size_t i = 0; i < h->d2h_begin.size(); ++i) {
-        const int b = h->d2h_begin[i], e = h->d2h_end[i];
-        RT_CHECK(cudaMemcpy2DAsync(h->h_jac + b, (size_t)h->K * 8, h->d_jac[h->ring] + b, (size_t)h->K * 8,
-                                   (size_t)(e - b) * 8, h->nn, cudaMemcpyDeviceToHost, h->stream));
-      }
+      if ((rc = enqueue_jac_copy(h, h->stream))) return rc;
+      RT_CHECK(cudaStreamSynchronize(h->stream));
     }
-    RT_CHECK(cudaStreamSynchronize(h->stream));
+    h->jac_cur = h->jac_target;
+    h->h_jac = h->h_jacs[h->jac_cur];
     h->jac_fetched = true;
   }
   if (jac_host && jac_host != h->h_jac) memcpy(jac_host, h->h_jac, bytes);
@@ -533,6 +600,11 @@ int opty_colloc_jacobian(opty_colloc_t* h, const double* free_host, double* jac_
 
 int opty_colloc_host_buffers(opty_colloc_t* h, double** free_pinned, double** con_pinned, double** jac_pinned) {
   if (!h) return fail(OPTY_ERR_ARG, "null handle");
+  if (jac_pinned) {
+    RT_CHECK(cudaSetDevice(h->cfg.device));
+    int rc = ensure_host_jac(h);
+    if (rc) return rc;
+  }
   if (free_pinned) *free_pinned = h->h_free;
   if (con_pinned) *con_pinned = h->h_con;
   if (jac_pinned) *jac_pinned = h->h_jac;
@@ -563,13 +635,17 @@ int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t*
     prev = col_end[i];
   }
   if (fill) {
+    int rcf = ensure_host_jac(h);
+    if (rcf) return rcf;
     // pre-write the per-node constant pattern once
-    for (int64_t i = 0; i < h->nn; ++i) memcpy(h->h_jac + i * h->K, fill, (size_t)h->K * 8);
+    for (int w = 0; w < 2; ++w)
+      if (h->h_jacs[w])
+        for (int64_t i = 0; i < h->nn; ++i) memcpy(h->h_jacs[w] + i * h->K, fill, (size_t)h->K * 8);
   }
   h->d2h_begin.swap(b);
   h->d2h_end.swap(e);
   h->jac_fetched = false;
-  if (!fill) h->full_fetch_needed = true;
+  if (!fill) h->full_fetch[0] = h->full_fetch[1] = true;
   return OPTY_OK;
 }
 

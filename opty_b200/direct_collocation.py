@@ -64,6 +64,7 @@ DEFAULT_CUDA_OPTIONS = {
     'out_ring': 1,              # device output sets to rotate through
     'use_sympy_cse': True,
     'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
+    'prefetch_jacobian': True,  # constraints() starts the Jacobian D2H early
     'target_warps': 148 * 16,
     'max_group_cost': 6000.0,
 }
@@ -309,10 +310,6 @@ class ConstraintCollocator(object):
         if len(set(names)) != len(names):
             raise ValueError('Repeated input trajectory variable fnames not '
                              'allowed: {}'.format(names))
-        if self._deriv_in_knw_traj:
-            raise NotImplementedError(
-                'Known trajectories that are implicit functions of time, '
-                'e.g. r(x(t)), are not supported by the cuda backend yet.')
         known, unknown = self._split_known(others,
                                            self._known_trajectory_map.keys())
         self._known_input_trajectories = known
@@ -337,10 +334,52 @@ class ConstraintCollocator(object):
         self._xp = tagged(self._state_symbols, 'p')
         self._xi = tagged(self._state_symbols, 'i')
         self._xn = tagged(self._state_symbols, 'n')
-        self._ki = tagged(self._known_input_trajectories, 'i')
-        self._kn = tagged(self._known_input_trajectories, 'n')
+        self._ki = tuple(self._discrete_known_input(f, 'i')
+                         for f in self._known_input_trajectories)
+        self._kn = tuple(self._discrete_known_input(f, 'n')
+                         for f in self._known_input_trajectories)
         self._ui = tagged(self._unknown_input_trajectories, 'i')
         self._un = tagged(self._unknown_input_trajectories, 'n')
+
+    def _discrete_known_input(self, f, tag):
+        """Discrete stand-in of a known input (opty/direct_collocation.py:
+        2080-2093): ``r(t) -> ri``; an implicit function of time ``r(x(t))``
+        stays a function ``ri(xi)`` so that differentiation applies the chain
+        rule; its user-supplied derivative ``dr/dx`` becomes the symbol
+        ``dri_dxi``."""
+        if isinstance(f, sm.Derivative):
+            var, (wrt, _) = f.args
+            return sm.Symbol('d{}{}_d{}{}'.format(
+                var.__class__.__name__, tag, wrt.__class__.__name__, tag),
+                real=True)
+        if f.args[0] != self._time_symbol:
+            inner = sm.Symbol(f.args[0].__class__.__name__ + tag, real=True)
+            return sm.Function(f.__class__.__name__ + tag, real=True)(inner)
+        return sm.Symbol(f.__class__.__name__ + tag, real=True)
+
+    def _chain_rules(self):
+        """``[(discrete function, discrete state symbol, derivative symbol)]``
+        for every implicit known trajectory ``r(x(t))``: the seed
+        ``d ri(xi) / d xi = dri_dxi`` of the forward-mode differentiation
+        (the reference reaches the same through SymPy's unevaluated
+        ``Derivative`` and the replacements of opty/direct_collocation.py:
+        2284-2302, 2760-2793)."""
+        rules = []
+        known = self._known_input_trajectories
+        for tag, symbols in (('i', self._ki), ('n', self._kn)):
+            for f, disc in zip(known, symbols):
+                if isinstance(f, sm.Derivative) or \
+                        f.args[0] == self._time_symbol:
+                    continue
+                deriv = f.diff(f.args[0])
+                if deriv not in known:
+                    raise ValueError(
+                        'The known trajectory {} is a function of {}; its '
+                        'derivative {} must be in known_trajectory_map too.'
+                        .format(f, f.args[0], deriv))
+                rules.append((disc, disc.args[0],
+                              symbols[known.index(deriv)]))
+        return rules
 
     def _discretize_eom(self):
         """Backward Euler: x' -> (xi - xp)/h, x -> xi, u -> ui.  Midpoint:
@@ -469,6 +508,13 @@ class ConstraintCollocator(object):
         uniform = list(self._parameters) + [self._time_interval_symbol]
         return rows, uniform, list(wrt)
 
+    def _build_program(self):
+        rows, uniform, wrt = self._program_inputs()
+        return CollocationProgram(
+            list(self.discrete_eom), rows, uniform, wrt,
+            use_sympy_cse=self._cuda_options['use_sympy_cse'],
+            chain_rules=self._chain_rules())
+
     def prepare_module(self):
         """Lowers, emits and compiles this problem's CUDA module without
         touching a GPU; returns the ``_PreparedModule``."""
@@ -589,6 +635,7 @@ def fill_kernel_config(cfg, meta, opts):
     cfg.tma_load = int(meta['tma_load'])
     cfg.tma_store = int(meta['tma_store'])
     cfg.out_ring = int(opts['out_ring'])
+    cfg.prefetch_jac = int(bool(opts.get('prefetch_jacobian', False)))
     for g, gm in enumerate(meta['groups']):
         cfg.group_col0[g] = gm['col0']
         cfg.group_ncols[g] = gm['ncols']
@@ -601,10 +648,8 @@ class _PreparedModule(object):
 
     def __init__(self, col):
         opts = col._cuda_options
-        rows, uniform, wrt = col._program_inputs()
         logger.info('Lowering and differentiating the constraint function.')
-        prog = CollocationProgram(list(col.discrete_eom), rows, uniform, wrt,
-                                  use_sympy_cse=opts['use_sympy_cse'])
+        prog = col._build_program()
         self.program = prog
         lo, hi = col._node_range
         (self.parts, self.derived, self.source, self.meta, self.cubin,

@@ -455,7 +455,7 @@ class Tape(object):
 # forward-mode differentiation on the tape
 # ---------------------------------------------------------------------------
 
-def forward_jacobian(tape, outputs, wrt_nodes):
+def forward_jacobian(tape, outputs, wrt_nodes, chain=None):
     """Sparse vector forward-mode derivative of ``outputs`` with respect to
     the input nodes ``wrt_nodes``.
 
@@ -466,12 +466,16 @@ def forward_jacobian(tape, outputs, wrt_nodes):
     does this with an explicit pruning pass; here unreachable derivative nodes
     are simply never emitted because the emitter walks from the outputs).
 
+    ``chain`` maps an input node that is itself a function of another input
+    (an implicit known trajectory ``r(x)``) to ``[(x node, dr/dx node)]``.
+
     Returns
     -------
     rows : list of dict
         ``rows[j][k]`` is the tape id of ``d outputs[j] / d wrt_nodes[k]``;
         missing keys are structural zeros.
     """
+    chain = chain or {}
     T = tape
     seeds = {}
     for k, w in enumerate(wrt_nodes):
@@ -502,8 +506,12 @@ def forward_jacobian(tape, outputs, wrt_nodes):
             continue
         if o == VIN or o == UIN:
             ks = seeds.get(i)
-            if ks:
-                d[i] = {k: T.one for k in ks}
+            row = {k: T.one for k in ks} if ks else {}
+            for var, deriv in chain.get(i, ()):
+                for k in seeds.get(var, ()):
+                    row[k] = deriv if k not in row else T.add(row[k], deriv)
+            if row:
+                d[i] = row
             continue
         a = a_[i]
         b = b_[i]

@@ -85,7 +85,7 @@ class CollocationProgram(object):
         return self
 
     def __init__(self, discrete_eom, traj_symbols, uniform_symbols, wrt,
-                 use_sympy_cse=True):
+                 use_sympy_cse=True, chain_rules=()):
         self.M = len(discrete_eom)
         self.P = len(wrt)
         self.K = self.M * self.P
@@ -105,7 +105,13 @@ class CollocationProgram(object):
         self.con = lower_matrix(T, leaf, list(discrete_eom),
                                 use_sympy_cse=use_sympy_cse)
         wrt_nodes = [leaf[w] for w in wrt]
-        rows = ir.forward_jacobian(T, self.con, wrt_nodes)
+        # implicit known trajectories r(x): d r / d x is another input row
+        chain = {}
+        for func, var, deriv in chain_rules:
+            if func in leaf and var in leaf:
+                chain.setdefault(leaf[func], []).append(
+                    (leaf[var], leaf[deriv]))
+        rows = ir.forward_jacobian(T, self.con, wrt_nodes, chain=chain)
         zero = T.zero
         # dense M x P table of tape ids, structural zeros point at literal 0
         self.jac = [[row.get(k, zero) for k in range(self.P)] for row in rows]

@@ -55,6 +55,7 @@ class ColloCfg(ctypes.Structure):
         ('out_ring', ctypes.c_int32),
         ('con_tail', ctypes.c_int32),
         ('jac_tail', ctypes.c_int32),
+        ('prefetch_jac', ctypes.c_int32),
         ('group_col0', ctypes.c_int32 * OPTY_MAX_GROUPS),
         ('group_ncols', ctypes.c_int32 * OPTY_MAX_GROUPS),
         ('h', ctypes.c_double),
@@ -159,16 +160,31 @@ class ColloHandle(object):
         self.jac_len = self.nn * self.K
         pf = ctypes.POINTER(ctypes.c_double)()
         pc = ctypes.POINTER(ctypes.c_double)()
-        pj = ctypes.POINTER(ctypes.c_double)()
         _check(self.lib, self.lib.opty_colloc_host_buffers(
-            self._h, ctypes.byref(pf), ctypes.byref(pc), ctypes.byref(pj)))
+            self._h, ctypes.byref(pf), ctypes.byref(pc), None))
         self.free_pinned = _view(pf, self.free_len)
         self.con_pinned = _view(pc, self.con_len + cfg.con_tail)
-        self.jac_pinned = _view(pj, self.jac_len + cfg.jac_tail)
+        self._jac_views = {}
+        self.jac_pinned = None    # pinned Jacobian buffers are lazy
+
+    def _current_jac_view(self):
+        """NumPy view of the pinned buffer that holds the most recently
+        fetched Jacobian (with speculative copies there are two buffers that
+        take turns)."""
+        pj = ctypes.POINTER(ctypes.c_double)()
+        _check(self.lib, self.lib.opty_colloc_host_buffers(
+            self._h, None, None, ctypes.byref(pj)))
+        addr = ctypes.addressof(pj.contents)
+        view = self._jac_views.get(addr)
+        if view is None:
+            view = _view(pj, self.jac_len + self.cfg.jac_tail)
+            self._jac_views[addr] = view
+        return view
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h:
             self.free_pinned = self.con_pinned = self.jac_pinned = None
+            self._jac_views = {}
             self.lib.opty_colloc_destroy(self._h)
             self._h = None
 
@@ -215,6 +231,7 @@ class ColloHandle(object):
         free = _as_f64(free, self.free_len, 'free')
         _check(self.lib, self.lib.opty_colloc_jacobian(
             self._h, free.ctypes.data, None))
+        self.jac_pinned = self._current_jac_view()
         return self.jac_pinned
 
     def device_buffers(self):

@@ -32,6 +32,7 @@ def ufuncify_matrix(args, expr, const=None, tmp_dir=None, parallel=False,
     const = tuple(const) if const is not None else ()
     opts = dict(DEFAULT_CUDA_OPTIONS)
     opts['d2h_skip_constants'] = False
+    opts['prefetch_jacobian'] = False
     if cuda_options:
         opts.update(cuda_options)
     prog = CollocationProgram.from_matrix(args, expr, const=const,

@@ -436,20 +436,27 @@ class OracleCollocator(object):
             wrt += (self.h_sym,)
         return wrt
 
-    def _loops(self):
+    def _constraint_loop(self):
         if self._con_loop is None:
-            const = self.pars + (self.h_sym,)
             self._con_loop = compile_matrix_function(
-                self._args(), self.discrete_eom, const=const,
-                parallel=self.parallel, build_dir=self.build_dir)
+                self._args(), self.discrete_eom,
+                const=self.pars + (self.h_sym,), parallel=self.parallel,
+                build_dir=self.build_dir)
+        return self._con_loop
+
+    def _jacobian_loop(self):
+        if self._jac_loop is None:
             partials = forward_jacobian(
                 sm.ImmutableDenseMatrix(self.discrete_eom),
                 sm.ImmutableDenseMatrix([list(self._wrt())]).T)
             self._jac_loop = compile_matrix_function(
-                self._args(), partials, const=const, parallel=self.parallel,
-                build_dir=self.build_dir)
+                self._args(), partials, const=self.pars + (self.h_sym,),
+                parallel=self.parallel, build_dir=self.build_dir)
             self._jac_buffer = np.empty((self.N - 1, self.M * self.P))
-        return self._con_loop, self._jac_loop
+        return self._jac_loop
+
+    def _loops(self):
+        return self._constraint_loop(), self._jacobian_loop()
 
     # -- numeric argument assembly (direct_collocation.py:2411-2437) --------
     def _numeric_args(self, free):
@@ -488,7 +495,7 @@ class OracleCollocator(object):
         """``[eom_1 @ nodes, ..., eom_M @ nodes, c_1..c_o]``
         (direct_collocation.py:2444-2446, 2985-2991)."""
         free = np.asarray(free, dtype=float)
-        con_loop, _ = self._loops()
+        con_loop = self._constraint_loop()
         result = np.empty((self.N - 1, self.M))
         vals = con_loop(result, *self._numeric_args(free))
         out = vals.reshape(self.N - 1, self.M).T.flatten()
@@ -500,7 +507,7 @@ class OracleCollocator(object):
         """Node-major partials then the instance entries
         (direct_collocation.py:2885-2887, 2985-2991)."""
         free = np.asarray(free, dtype=float)
-        _, jac_loop = self._loops()
+        jac_loop = self._jacobian_loop()
         vals = jac_loop(self._jac_buffer, *self._numeric_args(free)).ravel()
         if self.o:
             return np.hstack((vals, self._instance_jacobian_values(free)))

@@ -188,6 +188,72 @@ def single_eom():
                 expected_cols=None)
 
 
+def implicit_known_trajectory():
+    """Known trajectories that are implicit functions of time, theta(x(t)) and
+    omega(v(t)), given as callables of ``free`` together with their
+    derivatives; free node time interval; backward Euler, N = 4.
+    opty/tests/test_direct_collocation.py:18-212."""
+    import sympy.physics.mechanics as mech
+    m, g, r, h = sm.symbols('m, g, r, h', real=True)
+    x, v, f, s = mech.dynamicsymbols('x, v, f, s', real=True)
+    t = mech.dynamicsymbols._t
+    theta_of_x = sm.Function('theta', real=True)(x)
+    omega_of_v = sm.Function('omega', real=True)(v)
+    eom = sm.Matrix([x.diff() - v - s + r * omega_of_v,
+                     m * v.diff() - f + m * g * sm.sin(theta_of_x)])
+    N = 4
+    xs = np.linspace(2.0, 5.0, num=N)
+    ths = np.linspace(0.0, 10.0, num=N)
+
+    def calc_theta_x(free):
+        return np.interp(free[0:N], xs, ths)
+
+    def calc_dtheta_dx(free):
+        return np.array([3.9, 1.2, -5.6, 12.3])
+
+    def calc_omega_v(free):
+        return np.array([-0.01, -0.98, 3.45, 27.45])
+
+    def calc_domega_dv(free):
+        return np.array([0.1, 8.9, -43.4, -2.5])
+
+    traj_map = OrderedDict([
+        (omega_of_v.diff(v), calc_domega_dv), (omega_of_v, calc_omega_v),
+        (s, np.array([121., 122., 123., 124.])), (theta_of_x, calc_theta_x),
+        (theta_of_x.diff(x), calc_dtheta_dx)])
+    free = np.array([2., 3., 4., 5., 6., 7., 8., 9., 10., 11., 12., 13., 14.])
+    thetas, dthetas = calc_theta_x(free), calc_dtheta_dx(free)
+    omegas, domegas = calc_omega_v(free), calc_domega_dv(free)
+    con = np.array([
+        (3. - 2.) / 14. - 7. - 122. + 7.1 * omegas[1],
+        (4. - 3.) / 14. - 8. - 123. + 7.1 * omegas[2],
+        (5. - 4.) / 14. - 9. - 124. + 7.1 * omegas[3],
+        3.3 * (7. - 6.) / 14. - 11. + 3.3 * 10.2 * np.sin(thetas[1]),
+        3.3 * (8. - 7.) / 14. - 12. + 3.3 * 10.2 * np.sin(thetas[2]),
+        3.3 * (9. - 8.) / 14. - 13. + 3.3 * 10.2 * np.sin(thetas[3])])
+    jac = []
+    for i in (1, 2, 3):
+        xi, xp = free[i], free[i - 1]
+        vi, vp = free[N + i], free[N + i - 1]
+        jac += [1. / 14., -1. + 7.1 * domegas[i], -1. / 14., 0., 0.,
+                -(xi - xp) / 14.**2]
+        jac += [3.3 * 10.2 * np.cos(thetas[i]) * dthetas[i], 3.3 / 14., 0.,
+                -3.3 / 14., -1., -3.3 * (vi - vp) / 14.**2]
+    return Case(name='implicit_known_trajectory', eom=eom, states=(x, v), N=N,
+                h=h, method='backward euler', t=t,
+                par_map=OrderedDict([(r, 7.1), (m, 3.3), (g, 10.2)]),
+                traj_map=traj_map, instance_constraints=None, free=free,
+                expected_con=con, expected_jac=np.array(jac),
+                expected_rows=None, expected_cols=None)
+
+
+def product_cases():
+    """Cases for the CUDA path; the last one uses a reference feature the
+    oracle does not restate (implicit known trajectories), its expected values
+    are the reference test's closed-form numbers."""
+    return all_cases() + [implicit_known_trajectory()]
+
+
 def all_cases():
     return [msd_unknown_trajectory('backward euler'),
             msd_unknown_trajectory('midpoint'),

@@ -142,6 +142,37 @@ def test_constructor_errors():
                 0.01, time_symbol=t)
 
 
+def test_implicit_known_trajectory_symbols():
+    """opty/tests/test_direct_collocation.py:83-126."""
+    case = cases.implicit_known_trajectory()
+    col = ConstraintCollocator(*case.collocator_args(),
+                               **case.collocator_kwargs())
+    keys = list(case.traj_map.keys())
+    assert col._deriv_in_knw_traj
+    assert col.known_input_trajectories == tuple(keys)
+    assert [f.name for f in col.unknown_input_trajectories] == ['f']
+    xi = sm.Symbol('xi', real=True)
+    vi = sm.Symbol('vi', real=True)
+    assert col.current_known_discrete_specified_symbols == (
+        sm.Symbol('domegai_dvi', real=True),
+        sm.Function('omegai', real=True)(vi),
+        sm.Symbol('si', real=True),
+        sm.Function('thetai', real=True)(xi),
+        sm.Symbol('dthetai_dxi', real=True))
+    rules = col._chain_rules()
+    assert (sm.Function('thetai', real=True)(xi), xi,
+            sm.Symbol('dthetai_dxi', real=True)) in rules
+    # a function of two variables is rejected
+    x, v = case.states
+    th2 = sm.Function('theta', real=True)(x, v)
+    eom = case.eom.subs(sm.Function('theta', real=True)(x), th2)
+    with pytest.raises(ValueError):
+        ConstraintCollocator(eom, case.states, 4, case.h,
+                             known_parameter_map=case.par_map,
+                             known_trajectory_map={th2: np.ones(4)},
+                             time_symbol=case.t)
+
+
 def test_instance_constraint_indexing():
     case = cases.pendulum_variable_duration()
     col = ConstraintCollocator(*case.collocator_args(),
@@ -286,7 +317,8 @@ def test_emitted_code_matches_reference_golden(name, make, groups):
     assert_values_close(jac, gold['jac'][:nn * M * P], row_len=P)
 
 
-@pytest.mark.parametrize('case', cases.all_cases(), ids=lambda c: c.name)
+@pytest.mark.parametrize('case', cases.product_cases(),
+                         ids=lambda c: c.name)
 def test_emitted_code_known_answers(case):
     col = ConstraintCollocator(*case.collocator_args(),
                                **case.collocator_kwargs())
