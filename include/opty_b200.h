@@ -35,8 +35,9 @@
 extern "C" {
 #endif
 
-#define OPTY_B200_ABI_VERSION 2
+#define OPTY_B200_ABI_VERSION 3
 #define OPTY_MAX_GROUPS 64
+#define OPTY_MAX_SEGMENTS 128
 
 #define OPTY_OK 0
 #define OPTY_ERR_ARG -1     /* invalid argument / configuration */
@@ -72,15 +73,20 @@ typedef struct opty_colloc_cfg {
   int32_t tile_cols;        /* C: columns of the Jacobian staging tile */
   int32_t warps_per_block;
   int32_t pre_groups;       /* grid.y of the pre-pass kernel (groups of derived rows) */
-  int32_t tile_bufs;        /* staging tiles per warp (2..4) */
-  int32_t tma_load;         /* module was emitted with TMA input staging */
+  int32_t tile_bufs;        /* staging tiles per warp (1..4) */
+  int32_t tma_load;         /* input staging of the module: 1 TMA tile loads, 0 plain loads into shared
+                               memory, 2 none (lanes read the trajectory matrix directly) */
   int32_t tma_store;        /* module was emitted with TMA Jacobian stores */
   int32_t out_ring;         /* number of device output sets to rotate (>=1) */
   int32_t con_tail;         /* extra host slots after the M*(N-1) residuals */
   int32_t jac_tail;         /* extra host slots after the (N-1)*M*P partials */
   int32_t prefetch_jac;     /* opty_colloc_constraints starts the Jacobian D2H speculatively */
-  int32_t group_col0[OPTY_MAX_GROUPS];   /* first Jacobian column of group g */
-  int32_t group_ncols[OPTY_MAX_GROUPS];  /* number of columns of group g */
+  int32_t num_segments;     /* store segments: column runs of the node block written by the group bodies */
+  int32_t const_image_doubles; /* total length of the constant column runs that the pre-pass kernel
+                                  replicates into every node row (0: none); segments and constant
+                                  runs together tile the M*P columns */
+  int32_t seg_col0[OPTY_MAX_SEGMENTS];   /* first Jacobian column of segment s */
+  int32_t seg_ncols[OPTY_MAX_SEGMENTS];  /* number of columns of segment s */
   double h;                 /* fixed node time interval (ignored when s=1) */
 } opty_colloc_cfg;
 
@@ -143,6 +149,17 @@ int opty_colloc_device_buffers(opty_colloc_t* h, void** traj, int64_t* ldt, void
  * full copies. */
 int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t* col_begin,
                                 const int32_t* col_end, const double* fill);
+
+/* Registers the constant column runs of the node block (cfg.const_image_doubles
+ * columns in total): run i covers columns [col0[i], col0[i]+len[i]) (even start
+ * and length); `lit` / `inv_idx` give, in run order, each column's literal value
+ * or (inv_idx >= 0) its index in the node-invariant table.  These are the
+ * entries the reference recomputes for every node although they do not depend
+ * on it (opty/utils.py:483-494 evaluates the full matrix per node); here one
+ * image is replicated into all node rows by TMA tile stores.  Must be called
+ * once after opty_colloc_create when cfg.const_image_doubles > 0. */
+int opty_colloc_set_const_runs(opty_colloc_t* h, int num_runs, const int32_t* col0, const int32_t* len,
+                               const double* lit, const int32_t* inv_idx);
 
 /* CUDA-event duration (ms) of the kernels of the last evaluation. */
 int opty_colloc_last_kernel_ms(opty_colloc_t* h, float* ms);

@@ -34,7 +34,7 @@ import os
 
 from . import ir
 
-EMITTER_VERSION = 4
+EMITTER_VERSION = 5
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 KERNEL_HEADER = os.path.join(_HERE, 'csrc', 'colloc_kernel.cuh')
@@ -180,10 +180,15 @@ def choose_tile_cols(requested):
 
 def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 min_blocks_per_sm=4, tma_load=True, tma_store=True,
-                derived=(), debug_nostore=False, tile_bufs=2):
+                derived=(), debug_nostore=False, tile_bufs=2, debug_reps=1,
+                const_runs=()):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(r0, r1)`` EOM row ranges).  ``derived`` lists the tape ids
-    that the pre-pass kernel evaluates once per node into derived rows."""
+    that the pre-pass kernel evaluates once per node into derived rows.
+    ``const_runs`` lists ``(col0, length)`` column runs of the node block
+    whose entries are the same for every node: the group bodies skip them
+    and the runtime's replicator kernel copies one shared-memory image of
+    them into every node row with TMA tile stores."""
     T = prog.tape
     M, P, K, R = prog.M, prog.P, prog.K, prog.R
     C = choose_tile_cols(tile_cols)
@@ -194,10 +199,42 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     derived_index = {nid: k for k, nid in enumerate(derived)}
     D = len(derived)
 
+    const_runs = sorted(const_runs)
+    carved = [False] * K
+    for a, ln in const_runs:
+        assert a % 2 == 0 and ln % 2 == 0 and tma_store
+        for c in range(a, a + ln):
+            carved[c] = True
+    # store segments: maximal runs of non-carved columns inside one group;
+    # each gets its own TMA descriptor (box C x 32, clipped at the segment end)
+    segments = []          # (col0, ncols)
+    group_segments = []    # per group: list of segment ids
+    for (r0, r1) in groups:
+        ids = []
+        c = r0 * P
+        end = r1 * P
+        while c < end:
+            if carved[c]:
+                c += 1
+                continue
+            e = c
+            while e < end and not carved[e]:
+                e += 1
+            ids.append(len(segments))
+            segments.append((c, e - c))
+            c = e
+        group_segments.append(ids)
+    seg_of_col = {}
+    for sid, (a, ln) in enumerate(segments):
+        for c in range(a, a + ln):
+            seg_of_col[c] = sid
+    ncc = sum(ln for _, ln in const_runs)
+
     out = []
     w = out.append
     w('// generated by opty_b200.codegen (emitter v{}); do not edit'.format(
         EMITTER_VERSION))
+    w('#define OPTY_NSEGS {}'.format(max(len(segments), 1)))
     w('#define OPTY_M {}'.format(M))
     w('#define OPTY_P {}'.format(P))
     w('#define OPTY_K {}'.format(K))
@@ -209,11 +246,13 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     w('#define OPTY_NUNI {}'.format(max(prog.num_uniform, 1)))
     w('#define OPTY_WARPS {}'.format(warps_per_block))
     w('#define OPTY_MIN_BLOCKS {}'.format(min_blocks_per_sm))
-    w('#define OPTY_TMA_LOAD {}'.format(1 if tma_load else 0))
+    w('#define OPTY_TMA_LOAD {}'.format(int(tma_load)))
     w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
     w('#define OPTY_NBUF {}'.format(int(tile_bufs)))
     if debug_nostore:
         w('#define OPTY_DEBUG_NOSTORE {}'.format(int(debug_nostore)))
+    if debug_reps != 1:
+        w('#define OPTY_DEBUG_REPS {}'.format(int(debug_reps)))
     w('#include "colloc_kernel.cuh"')
     w('')
 
@@ -243,6 +282,20 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     for ks in by_arg.values():
         pre_chunks.append(ks)
     pre_groups = len(pre_chunks)
+    # pattern of the constant runs (replicated into every node row by the
+    # runtime's opty_replicate_kernel): literal value, or index into the
+    # node-invariant table, in run order
+    const_lit, const_inv = [], []
+    for a, ln in const_runs:
+        for c in range(a, a + ln):
+            e = prog.jac[c // P][c % P]
+            if T.op[e] == ir.CONST:
+                const_lit.append(float(T.val[e]))
+                const_inv.append(-1)
+            else:
+                assert not T.varying[e]
+                const_lit.append(0.0)
+                const_inv.append(prog.inv_index[e])
     w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
     w('opty_colloc_pre(const OptyParams p)')
     w('{')
@@ -269,18 +322,28 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     for g, (r0, r1) in enumerate(groups):
         bw = _BodyWriter(prog, 'main', derived_index)
         body = bw.lines
-        col0 = r0 * P
-        ncols = (r1 - r0) * P
         w('static __device__ __forceinline__ void opty_group_{}('
           'const OptyCtx& ctx)'.format(g))
         w('{')
-        cc = 0          # group-relative column of the next Jacobian entry
-        chunk = 0
-        pending = None  # first half of a 16-byte pair
+        state = {'seg': None, 'cc': 0, 'chunk': 0, 'pending': None,
+                 'stored': 0}
 
-        def flush(ncols_in_chunk):
-            body.append('OPTY_FLUSH({}, {}, {}, {});'.format(
-                g, chunk, col0, ncols_in_chunk))
+        def flush():
+            sid = state['seg']
+            cc = state['cc']
+            ncols_in_chunk = cc % C or C
+            q = (cc - 1) // C
+            body.append('OPTY_FLUSH({}, {}, {}, {}, {});'.format(
+                sid, q, state['chunk'] % tile_bufs, segments[sid][0],
+                ncols_in_chunk))
+            state['chunk'] += 1
+
+        def close_segment():
+            assert state['pending'] is None
+            if state['seg'] is not None and state['cc'] % C != 0:
+                flush()
+            state['seg'] = None
+            state['cc'] = 0
 
         for j in range(r0, r1):
             if prog.con:
@@ -288,35 +351,44 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 body.append('OPTY_CON({}, {});'.format(
                     j, bw.ref(prog.con[j])))
             for k in range(P):
+                col = j * P + k
+                if carved[col]:
+                    continue
+                sid = seg_of_col[col]
+                if sid != state['seg']:
+                    close_segment()
+                    state['seg'] = sid
+                seg_ncols = segments[sid][1]
                 e = prog.jac[j][k]
                 bw.need(e)
+                cc = state['cc']
                 tc = cc % C
+                buf = state['chunk'] % tile_bufs
+                pending = state['pending']
                 if pending is None and tc % 2 == 0 and tc + 1 < C and \
-                        cc + 1 < ncols:
-                    pending = (tc, bw.ref(e))
+                        cc + 1 < seg_ncols:
+                    state['pending'] = (tc, bw.ref(e))
                 elif pending is not None:
                     body.append('OPTY_JS2({}, {}, {}, {});'.format(
-                        chunk % tile_bufs, pending[0], pending[1],
-                        bw.ref(e)))
-                    pending = None
+                        buf, pending[0], pending[1], bw.ref(e)))
+                    state['pending'] = None
                 else:
                     body.append('OPTY_JS1({}, {}, {});'.format(
-                        chunk % tile_bufs, tc, bw.ref(e)))
-                cc += 1
-                if cc % C == 0 and pending is None:
-                    flush(C)
-                    chunk += 1
-        assert pending is None
-        if cc % C != 0:
-            flush(cc % C)
-            chunk += 1
+                        buf, tc, bw.ref(e)))
+                state['cc'] = cc + 1
+                state['stored'] += 1
+                if state['cc'] % C == 0 and state['pending'] is None:
+                    flush()
+        close_segment()
         body.append('OPTY_DRAIN();')
         for line in body:
             w('  ' + line)
         w('}')
         w('')
-        group_meta.append({'rows': [r0, r1], 'col0': col0, 'ncols': ncols,
-                           'ops': bw.num_ops, 'chunks': chunk})
+        group_meta.append({'rows': [r0, r1], 'col0': r0 * P,
+                           'ncols': state['stored'],
+                           'segments': group_segments[g],
+                           'ops': bw.num_ops, 'chunks': state['chunk']})
 
     # blockIdx.y -> group: most expensive groups are launched first
     order = sorted(range(len(groups)),
@@ -331,6 +403,11 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
       'const OptyParams p)')
     w('{')
     w('  OPTY_KERNEL_BEGIN()')
+    if debug_reps != 1:
+        # measurement aid: the same tile is evaluated several times, passes
+        # after the first find the group body in the instruction caches
+        w('#pragma unroll 1')
+        w('  for (int opty_rep = 0; opty_rep < OPTY_DEBUG_REPS; ++opty_rep)')
     w('  switch (opty_g) {')
     for g in range(len(groups)):
         w('    case {}: opty_group_{}(ctx); break;'.format(g, g))
@@ -345,6 +422,11 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         'M': M, 'P': P, 'K': K, 'R': R, 'C': C, 'D': D,
         'num_groups': len(groups),
         'groups': group_meta,
+        'segments': [list(sg) for sg in segments],
+        'const_runs': [list(cr) for cr in const_runs],
+        'const_image_doubles': ncc,
+        'const_lit': const_lit,
+        'const_inv': const_inv,
         'num_inv': ninv,
         'num_uniform': prog.num_uniform,
         'inv_ops': inv_ops,
@@ -353,7 +435,7 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         'group_order': order,
         'warps_per_block': warps_per_block,
         'min_blocks_per_sm': min_blocks_per_sm,
-        'tma_load': bool(tma_load),
+        'tma_load': int(tma_load),
         'tma_store': bool(tma_store),
         'tile_bufs': int(tile_bufs),
         'method': method,

@@ -60,7 +60,8 @@
 
 struct OptyTmaps {
   CUtensorMap in;                 // traj as {cols, R + D}
-  CUtensorMap out[OPTY_NGROUPS];  // group g's columns of jac as {ncols_g, nodes}
+  CUtensorMap out[OPTY_NSEGS];    // store segment s (a run of columns written by one group) of jac as
+                                  // {ncols_s, nodes}
 };
 
 // node-invariant sub-expressions, filled by the host from opty_colloc_inv
@@ -68,7 +69,9 @@ __constant__ double opty_ci[OPTY_NINV];
 #define CI(k) opty_ci[k]
 
 struct OptyCtx {
-  const double* xs;  // this lane's column in its staged segment; row pitch OPTY_XBOX
+  const double* xs;  // this lane's column in its staged segment (row pitch OPTY_XBOX) or, with direct
+                     // input loads, in the trajectory matrix itself (row pitch ldt)
+  long long ldt;
   double* con;       // &con[node of this lane]
   double* trow0;     // this lane's row in tile buffer 0 (buffer b: + b*OPTY_TILE_DOUBLES)
   double* tile0;     // warp's tile buffer 0
@@ -133,9 +136,17 @@ static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map,
 // ---------------------------------------------------------------------------
 // trajectory value of row r at this lane's node (A) and at the next node (B);
 // derived row d (pre-pass output) at this lane's node
+#if OPTY_TMA_LOAD == 2
+// direct mode: no staging; lanes read consecutive columns of a row (coalesced,
+// read-only path), the neighbour column comes from the same cache lines
+#define XA(r) __ldg(ctx.xs + (long long)(r) * ctx.ldt)
+#define XB(r) __ldg(ctx.xs + (long long)(r) * ctx.ldt + 1)
+#define XD(d) __ldg(ctx.xs + (long long)(OPTY_R + (d)) * ctx.ldt)
+#else
 #define XA(r) ctx.xs[(r) * OPTY_XBOX]
 #define XB(r) ctx.xs[(r) * OPTY_XBOX + 1]
 #define XD(d) ctx.xs[(OPTY_R + (d)) * OPTY_XBOX]
+#endif
 
 #define OPTY_CON(j, val)                                       \
   do {                                                         \
@@ -146,12 +157,13 @@ static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map,
 #define OPTY_JS2(buf, tc, v0, v1) *reinterpret_cast<double2*>(OPTY_TROW(buf) + (tc)) = make_double2((v0), (v1))
 #define OPTY_JS1(buf, tc, v0) OPTY_TROW(buf)[(tc)] = (v0)
 
-// Hands the warp's finished tile (chunk `q` of group `g`: node rows
-// ctx.node..+31, Jacobian columns col0 + q*C .. + ncols) to the TMA unit, or
-// copies it out with coalesced warp-per-node stores.
-template <int G, int Q, int COL0, int NCOLS>
+// Hands the warp's finished tile (chunk `Q` of store segment `SEG`: node rows
+// ctx.node..+31, Jacobian columns SEGCOL0 + Q*C .. + NCOLS, staged in tile
+// buffer `BUF`) to the TMA unit, or copies it out with coalesced
+// warp-per-node stores.
+template <int SEG, int Q, int BUF, int SEGCOL0, int NCOLS>
 static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
-  double* tile = ctx.tile0 + (Q % OPTY_NBUF) * OPTY_TILE_DOUBLES;
+  double* tile = ctx.tile0 + BUF * OPTY_TILE_DOUBLES;
 #if OPTY_TMA_STORE
   // make the generic-proxy st.shared visible to the async proxy, then one
   // lane issues the tile store; at most OPTY_NBUF-1 older stores may still be
@@ -162,7 +174,7 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   // 2 = all tile stores go to node rows 0..31 (no HBM write stream),
   // 3 = stores without waiting for the staging buffer to be free again
   if (ctx.lane == 0 && ctx.node < ctx.n_nodes && OPTY_DEBUG_NOSTORE != 1) {
-    opty_tma_store_2d(&ctx.tm->out[G], tile, Q * OPTY_C, OPTY_DEBUG_NOSTORE == 2 ? 0 : ctx.node);
+    opty_tma_store_2d(&ctx.tm->out[SEG], tile, Q * OPTY_C, OPTY_DEBUG_NOSTORE == 2 ? 0 : ctx.node);
     if (OPTY_DEBUG_NOSTORE != 3) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(OPTY_NBUF - 1) : "memory");
   }
   __syncwarp();
@@ -170,7 +182,7 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   __syncwarp();
   const int rows = min(32, ctx.n_nodes - ctx.node);
   for (int r = 0; r < rows; ++r) {
-    double* dst = ctx.jac + (long long)(ctx.node + r) * OPTY_K + COL0 + Q * OPTY_C;
+    double* dst = ctx.jac + (long long)(ctx.node + r) * OPTY_K + SEGCOL0 + Q * OPTY_C;
     const double* src = tile + r * OPTY_C;
 #pragma unroll
     for (int c = 0; c < NCOLS; c += 32)
@@ -179,7 +191,7 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   __syncwarp();
 #endif
 }
-#define OPTY_FLUSH(g, q, col0, ncols) opty_flush<g, q, col0, ncols>(ctx)
+#define OPTY_FLUSH(seg, q, buf, segcol0, ncols) opty_flush<seg, q, buf, segcol0, ncols>(ctx)
 
 // end of a group body: the warp's tile buffers are reused by its next tile
 #if OPTY_TMA_STORE
@@ -197,10 +209,16 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
 // dynamic shared memory: [WARPS][NBUF][32][C] Jacobian tiles | [NSEG][R+D][XBOX]
 // trajectory segments | mbarrier, tile slot
 #define OPTY_SMEM_TILES_BYTES (OPTY_WARPS * OPTY_NBUF * OPTY_TILE_DOUBLES * 8)
+#if OPTY_TMA_LOAD == 2
+#define OPTY_SMEM_XIN_BYTES 0
+#else
 #define OPTY_SMEM_XIN_BYTES (OPTY_NSEG * OPTY_XSEG_BYTES)
+#endif
 #define OPTY_SMEM_BYTES (OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES + 128)
 
-#if OPTY_TMA_LOAD
+#if OPTY_TMA_LOAD == 2
+#define OPTY_STAGE_INPUT()
+#elif OPTY_TMA_LOAD == 1
 #define OPTY_STAGE_INPUT()                                                                               \
   if (threadIdx.x == 0) {                                                                                \
     opty_mbar_expect_tx(bar, OPTY_NSEG * OPTY_RD * OPTY_XBOX * 8);                                       \
@@ -238,16 +256,22 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(opty_smem + OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES);  \
   uint32_t phase = 0;                                                                                    \
   (void)phase;                                                                                           \
-  if (threadIdx.x == 0 && OPTY_TMA_LOAD) opty_mbar_init(bar, 1);                                         \
-  __syncthreads();                                                                                       \
+  if (OPTY_TMA_LOAD == 1) {                                                                              \
+    if (threadIdx.x == 0) opty_mbar_init(bar, 1);                                                        \
+    __syncthreads();                                                                                     \
+  }                                                                                                      \
   const int opty_g = opty_group_order[blockIdx.y];                                                       \
   const int tile_node0 = blockIdx.x * OPTY_THREADS;                                                      \
   OPTY_STAGE_INPUT()                                                                                     \
   OptyCtx ctx;                                                                                           \
   ctx.lane = threadIdx.x & 31;                                                                           \
   ctx.n_nodes = p.n_nodes;                                                                               \
-  ctx.xs = reinterpret_cast<const double*>(xin_bytes + (threadIdx.x / OPTY_XSEG) * OPTY_XSEG_BYTES) +    \
-           (threadIdx.x % OPTY_XSEG);                                                                    \
+  ctx.ldt = p.ldt;                                                                                       \
+  if (OPTY_TMA_LOAD == 2)                                                                                \
+    ctx.xs = p.traj + min(tile_node0 + (int)threadIdx.x, p.n_nodes - 1);                                 \
+  else                                                                                                   \
+    ctx.xs = reinterpret_cast<const double*>(xin_bytes + (threadIdx.x / OPTY_XSEG) * OPTY_XSEG_BYTES) +  \
+             (threadIdx.x % OPTY_XSEG);                                                                  \
   ctx.ldc = p.ldc;                                                                                       \
   ctx.tile0 = tiles + (threadIdx.x >> 5) * OPTY_NBUF * OPTY_TILE_DOUBLES;                                \
   ctx.trow0 = ctx.tile0 + ctx.lane * OPTY_C;                                                             \
@@ -273,3 +297,4 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   const double* xg = p.traj + node;                             \
   double* drv = p.traj + (long long)OPTY_R * p.ldt + node;      \
   const int opty_pg = blockIdx.y;
+

@@ -139,6 +139,103 @@ __global__ void opty_jac_indices_kernel(long long first, long long count, long l
   }
 }
 
+
+// ---- constant-run replicator ------------------------------------------------
+// Column runs of the node block whose entries are literals or node-invariant
+// are the same for every node (at the 10-link pendulum: the 506 partials of
+// the 11 kinematic equations, half of all columns).  The generated group bodies
+// skip them; this kernel builds one shared-memory image [rows][w] of a chunk
+// (<= 254 columns of one run) and replicates it down the node rows with 2-D
+// TMA tile stores (32 KB per store): no per-node arithmetic, no per-node
+// staging, long contiguous row segments.  grid = (node-tile batches, chunks).
+#define OPTY_REPL_THREADS 128
+#define OPTY_REPL_MAX_CHUNKS 96
+struct OptyReplMaps {
+  CUtensorMap m[OPTY_REPL_MAX_CHUNKS];  // chunk c of jac as {w_c, nodes}, box {w_c, rows}
+};
+
+__global__ void __launch_bounds__(OPTY_REPL_THREADS)
+opty_replicate_kernel(const __grid_constant__ OptyReplMaps maps, const double* __restrict__ lit,
+                      const int* __restrict__ inv_idx, const double* __restrict__ inv,
+                      const int* __restrict__ ch_off, const int* __restrict__ ch_w, int n_nodes, int rows,
+                      int tiles_per_block) {
+  extern __shared__ __align__(128) unsigned char repl_smem[];
+  double* img = reinterpret_cast<double*>(repl_smem);
+  const int c = blockIdx.y;
+  const int w = ch_w[c];
+  const int off = ch_off[c];
+  for (int j = threadIdx.x; j < w; j += OPTY_REPL_THREADS) {
+    const int k = inv_idx[off + j];
+    const double v = k >= 0 ? inv[k] : lit[off + j];
+    for (int r = 0; r < rows; ++r) img[r * w + j] = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(img);
+    for (int t = 0; t < tiles_per_block; ++t) {
+      const int node0 = (blockIdx.x * tiles_per_block + t) * rows;
+      if (node0 >= n_nodes) break;
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                       reinterpret_cast<uint64_t>(&maps.m[c])),
+                   "r"(0), "r"(node0), "r"(src)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+// Same job with plain coalesced 16-byte stores: a warp writes a node row's run
+// as consecutive 512-byte pieces straight from the shared-memory image (the
+// fill pattern that reaches the measured HBM write ceiling).  grid.x = batches
+// of `nodes_per_block` nodes.
+__global__ void __launch_bounds__(OPTY_REPL_THREADS)
+opty_replicate_st_kernel(double* __restrict__ jac, long long K, const double* __restrict__ lit,
+                         const int* __restrict__ inv_idx, const double* __restrict__ inv,
+                         const int* __restrict__ run_col0, const int* __restrict__ run_len,
+                         const int* __restrict__ run_off, int num_runs, int ncc, int n_nodes,
+                         int nodes_per_block) {
+  extern __shared__ __align__(128) unsigned char repl_smem[];
+  double* img = reinterpret_cast<double*>(repl_smem);
+  int* tab = reinterpret_cast<int*>(img + ncc);  // [3][num_runs]: col0, len, off
+  for (int j = threadIdx.x; j < ncc; j += OPTY_REPL_THREADS) {
+    const int k = inv_idx[j];
+    img[j] = k >= 0 ? inv[k] : lit[j];
+  }
+  for (int r = threadIdx.x; r < num_runs; r += OPTY_REPL_THREADS) {
+    tab[r] = run_col0[r];
+    tab[num_runs + r] = run_len[r];
+    tab[2 * num_runs + r] = run_off[r];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int node_end = min(n_nodes, (int)(blockIdx.x + 1) * nodes_per_block);
+  for (int r = 0; r < num_runs; ++r) {
+    const int col0 = tab[r];
+    const int n2 = tab[num_runs + r] >> 1;
+    const double2* src = reinterpret_cast<const double2*>(img + tab[2 * num_runs + r]);
+    // a lane keeps its 16-byte pieces of the run in registers across the nodes it writes
+    for (int j0 = 0; j0 < n2; j0 += 32 * 8) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u * 32 + lane;
+        v[u] = j < n2 ? src[j] : make_double2(0.0, 0.0);
+      }
+      for (int node = blockIdx.x * nodes_per_block + warp; node < node_end; node += OPTY_REPL_THREADS / 32) {
+        double2* dst = reinterpret_cast<double2*>(jac + (long long)node * K + col0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + u * 32 + lane;
+          if (j < n2) dst[j] = v[u];
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 struct opty_colloc {
@@ -188,6 +285,26 @@ struct opty_colloc {
   bool evaluated = false;
   bool con_fetched = false, jac_fetched = false;
 
+  // constant-run replicator
+  int repl_chunks = 0;                 // 0: no constant runs registered
+  int repl_mode = 0;                   // 0: coalesced stores, 1: TMA tile stores
+  int repl_runs = 0;
+  int repl_nodes_per_block = 32;
+  int* d_run_col0 = nullptr;
+  int* d_run_len = nullptr;
+  int* d_run_off = nullptr;
+  int repl_rows = 16;                  // node rows per TMA store
+  int repl_tiles_per_block = 4;
+  size_t repl_smem = 0;
+  std::vector<int32_t> repl_col0, repl_w, repl_off;   // per chunk
+  double* d_repl_lit = nullptr;
+  int* d_repl_inv = nullptr;
+  int* d_repl_off = nullptr;
+  int* d_repl_w = nullptr;
+  std::vector<OptyReplMaps> repl_maps;  // per ring slot
+  cudaStream_t repl_stream = nullptr;
+  cudaEvent_t ev_repl_go = nullptr, ev_repl_done = nullptr;
+
   std::vector<int32_t> d2h_begin, d2h_end;
   unsigned smem_bytes = 0;
   unsigned grid_x = 0;
@@ -213,10 +330,10 @@ int encode_2d(CUtensorMap* map, void* base, uint64_t dim0, uint64_t dim1, uint64
 int build_tmaps(opty_colloc* h, int slot) {
   const opty_colloc_cfg& c = h->cfg;
   std::vector<unsigned char>& blob = h->tmaps[slot];
-  blob.assign(sizeof(CUtensorMap) * (1 + c.num_groups), 0);
+  blob.assign(sizeof(CUtensorMap) * (1 + (c.num_segments > 0 ? c.num_segments : 1)), 0);
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(blob.data());
   int rc;
-  if (c.tma_load) {
+  if (c.tma_load == 1) {
     const uint32_t threads = 32u * c.warps_per_block;
     const uint32_t xbox = (threads <= 128u ? threads : 128u) + 2u;
     if ((rc = encode_2d(&maps[0], h->d_traj, (uint64_t)h->ncols, (uint64_t)h->RD, (uint64_t)h->ldt * 8, xbox,
@@ -224,8 +341,8 @@ int build_tmaps(opty_colloc* h, int slot) {
       return rc;
   }
   if (c.tma_store) {
-    for (int g = 0; g < c.num_groups; ++g) {
-      if ((rc = encode_2d(&maps[1 + g], h->d_jac[slot] + c.group_col0[g], (uint64_t)c.group_ncols[g],
+    for (int g = 0; g < c.num_segments; ++g) {
+      if ((rc = encode_2d(&maps[1 + g], h->d_jac[slot] + c.seg_col0[g], (uint64_t)c.seg_ncols[g],
                           (uint64_t)h->nn, (uint64_t)h->K * 8, (uint32_t)c.tile_cols, 32u)))
         return rc;
     }
@@ -253,6 +370,30 @@ int launch_eval(opty_colloc* h) {
   }
   h->inv_dirty = false;
   h->ring = (h->ring + 1) % c.out_ring;
+  if (c.const_image_doubles > 0) {
+    if (h->repl_chunks == 0)
+      return fail(OPTY_ERR_STATE, "opty_colloc_set_const_runs must be called before evaluating");
+    // the replicator only depends on the invariants table: it runs on its own stream, next to the
+    // pre-pass and the main kernel, and is joined below
+    RT_CHECK(cudaEventRecord(h->ev_repl_go, h->stream));
+    RT_CHECK(cudaStreamWaitEvent(h->repl_stream, h->ev_repl_go, 0));
+    if (h->repl_mode == 1) {
+      const int n_tiles = (h->nn + h->repl_rows - 1) / h->repl_rows;
+      dim3 grid((unsigned)((n_tiles + h->repl_tiles_per_block - 1) / h->repl_tiles_per_block),
+                (unsigned)h->repl_chunks);
+      opty_replicate_kernel<<<grid, OPTY_REPL_THREADS, h->repl_smem, h->repl_stream>>>(
+          h->repl_maps[h->ring], h->d_repl_lit, h->d_repl_inv, h->d_inv, h->d_repl_off, h->d_repl_w, h->nn,
+          h->repl_rows, h->repl_tiles_per_block);
+    } else {
+      const unsigned blocks = (unsigned)((h->nn + h->repl_nodes_per_block - 1) / h->repl_nodes_per_block);
+      opty_replicate_st_kernel<<<blocks, OPTY_REPL_THREADS, (size_t)c.const_image_doubles * 8 + (size_t)h->repl_runs * 12, h->repl_stream>>>(
+          h->d_jac[h->ring], (long long)h->K, h->d_repl_lit, h->d_repl_inv, h->d_inv, h->d_run_col0, h->d_run_len,
+          h->d_run_off, h->repl_runs, c.const_image_doubles, h->nn, h->repl_nodes_per_block);
+    }
+    RT_CHECK(cudaGetLastError());
+    RT_CHECK(cudaEventRecord(h->ev_repl_done, h->repl_stream));
+    h->launches++;
+  }
   OptyParams p;
   p.traj = h->d_traj;
   p.con = h->d_con[h->ring];
@@ -271,6 +412,7 @@ int launch_eval(opty_colloc* h) {
   DRV_CHECK(g_drv.LaunchKernel(h->f_eval, h->grid_x, (unsigned)c.num_groups, 1, 32u * c.warps_per_block, 1, 1, h->smem_bytes,
                                (CUstream)h->stream, args, nullptr));
   h->launches++;
+  if (c.const_image_doubles > 0) RT_CHECK(cudaStreamWaitEvent(h->stream, h->ev_repl_done, 0));
   RT_CHECK(cudaEventRecord(h->ev1, h->stream));
   h->have_ms = true;
   h->evaluated = true;
@@ -363,7 +505,7 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
     return fail(OPTY_ERR_ARG, "invalid kernel geometry");
   if (cfg->out_ring < 1 || cfg->out_ring > 64) return fail(OPTY_ERR_ARG, "invalid out_ring");
   if (cfg->num_derived < 0 || cfg->pre_groups < 0 || (cfg->num_derived > 0 && cfg->pre_groups < 1) ||
-      cfg->tile_bufs < 2 || cfg->tile_bufs > 4)
+      cfg->tile_bufs < 1 || cfg->tile_bufs > 4)
     return fail(OPTY_ERR_ARG, "invalid num_derived / pre_groups / tile_bufs");
   const int expectP = (cfg->method == OPTY_MIDPOINT ? 2 * cfg->n + 2 * cfg->q : 2 * cfg->n + cfg->q) + cfg->r + cfg->s;
   if (cfg->method != OPTY_MIDPOINT && cfg->method != OPTY_BACKWARD_EULER && !elementwise)
@@ -371,12 +513,19 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   if (!elementwise && cfg->P != expectP)
     return fail(OPTY_ERR_ARG, "P does not match n, q, r, s and the integration method");
   {
-    long long covered = 0;
-    for (int g = 0; g < cfg->num_groups; ++g) {
-      if (cfg->group_col0[g] != covered || cfg->group_ncols[g] < 1) return fail(OPTY_ERR_ARG, "groups must tile the K columns");
-      covered += cfg->group_ncols[g];
+    if (cfg->num_segments < 0 || cfg->num_segments > OPTY_MAX_SEGMENTS || cfg->const_image_doubles < 0)
+      return fail(OPTY_ERR_ARG, "invalid segment count");
+    long long covered = cfg->const_image_doubles, prev_end = 0;
+    for (int g = 0; g < cfg->num_segments; ++g) {
+      if (cfg->seg_col0[g] < prev_end || cfg->seg_ncols[g] < 1)
+        return fail(OPTY_ERR_ARG, "store segments must be sorted, non-empty and disjoint");
+      prev_end = (long long)cfg->seg_col0[g] + cfg->seg_ncols[g];
+      covered += cfg->seg_ncols[g];
     }
-    if (covered != (long long)cfg->M * cfg->P) return fail(OPTY_ERR_ARG, "groups must tile the K columns");
+    if (prev_end > (long long)cfg->M * cfg->P || covered != (long long)cfg->M * cfg->P)
+      return fail(OPTY_ERR_ARG, "store segments and constant runs must tile the M*P columns");
+    if (cfg->const_image_doubles > 0 && !cfg->tma_store)
+      return fail(OPTY_ERR_ARG, "constant runs need TMA stores (even M*P)");
   }
 
   int ndev = 0;
@@ -398,7 +547,7 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   h->K = cfg->M * cfg->P;
   h->ldt = round_up(h->ncols, 16);
   h->free_len = (size_t)(cfg->n + cfg->q) * cfg->N + cfg->r + cfg->s;
-  if (cfg->tma_load && h->RD > 256) {
+  if (cfg->tma_load == 1 && h->RD > 256) {
     delete h;
     return fail(OPTY_ERR_ARG, "TMA input staging supports at most 256 trajectory rows");
   }
@@ -435,6 +584,9 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   CREATE_RT(cudaEventCreate(&h->ev1));
   CREATE_RT(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
   CREATE_RT(cudaEventCreateWithFlags(&h->ev_con, cudaEventDisableTiming));
+  CREATE_RT(cudaStreamCreateWithFlags(&h->repl_stream, cudaStreamNonBlocking));
+  CREATE_RT(cudaEventCreateWithFlags(&h->ev_repl_go, cudaEventDisableTiming));
+  CREATE_RT(cudaEventCreateWithFlags(&h->ev_repl_done, cudaEventDisableTiming));
 
   CREATE_RT(cudaMalloc(&h->d_traj, (size_t)h->RD * h->ldt * 8));
   CREATE_RT(cudaMemsetAsync(h->d_traj, 0, (size_t)h->RD * h->ldt * 8, h->stream));
@@ -464,13 +616,20 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   const unsigned threads = 32u * cfg->warps_per_block;
   const unsigned xseg = threads <= 128u ? threads : 128u;
   const unsigned nseg = threads / xseg;
-  const unsigned xin_bytes = nseg * (unsigned)round_up((int64_t)h->RD * (xseg + 2u) * 8, 128);
+  const unsigned xin_bytes =
+      cfg->tma_load == 2 ? 0u : nseg * (unsigned)round_up((int64_t)h->RD * (xseg + 2u) * 8, 128);
   h->smem_bytes = tiles_bytes + xin_bytes + 128u;
+  if (const char* pad = getenv("OPTY_B200_DEBUG_SMEM_FLOOR")) {
+    // measurement aid: a larger dynamic shared-memory request caps the resident blocks per SM
+    const unsigned floor_bytes = (unsigned)atoi(pad);
+    if (floor_bytes > h->smem_bytes) h->smem_bytes = floor_bytes;
+  }
   if (h->smem_bytes > 227u * 1024u) {
     opty_colloc_destroy(h);
     return fail(OPTY_ERR_ARG, "kernel needs more than 227 KB of shared memory per block");
   }
   CREATE_DRV(g_drv.FuncSetAttribute(h->f_eval, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)h->smem_bytes));
+
   h->n_tiles = (h->nn + 32 * cfg->warps_per_block - 1) / (32 * cfg->warps_per_block);
   h->grid_x = (unsigned)h->n_tiles;
   CREATE_RT(cudaStreamSynchronize(h->stream));
@@ -483,6 +642,17 @@ int opty_colloc_destroy(opty_colloc_t* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->repl_stream) cudaStreamSynchronize(h->repl_stream);
+  cudaFree(h->d_repl_lit);
+  cudaFree(h->d_repl_inv);
+  cudaFree(h->d_repl_off);
+  cudaFree(h->d_repl_w);
+  cudaFree(h->d_run_col0);
+  cudaFree(h->d_run_len);
+  cudaFree(h->d_run_off);
+  if (h->ev_repl_go) cudaEventDestroy(h->ev_repl_go);
+  if (h->ev_repl_done) cudaEventDestroy(h->ev_repl_done);
+  if (h->repl_stream) cudaStreamDestroy(h->repl_stream);
   for (double* p : h->d_con) cudaFree(p);
   for (double* p : h->d_jac) cudaFree(p);
   cudaFree(h->d_traj);
@@ -646,6 +816,99 @@ int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t*
   h->d2h_end.swap(e);
   h->jac_fetched = false;
   if (!fill) h->full_fetch[0] = h->full_fetch[1] = true;
+  return OPTY_OK;
+}
+
+int opty_colloc_set_const_runs(opty_colloc_t* h, int num_runs, const int32_t* col0, const int32_t* len,
+                               const double* lit, const int32_t* inv_idx) {
+  if (!h || num_runs < 1 || !col0 || !len || !lit || !inv_idx) return fail(OPTY_ERR_ARG, "invalid argument");
+  const opty_colloc_cfg& c = h->cfg;
+  if (!c.tma_store) return fail(OPTY_ERR_ARG, "constant runs need TMA stores (even M*P)");
+  RT_CHECK(cudaSetDevice(c.device));
+  long long total = 0;
+  int prev_end = 0;
+  std::vector<int32_t> ch_col0, ch_w, ch_off;
+  for (int r = 0; r < num_runs; ++r) {
+    if (col0[r] < prev_end || len[r] < 2 || (col0[r] & 1) || (len[r] & 1) || col0[r] + len[r] > h->K)
+      return fail(OPTY_ERR_ARG, "constant runs must be sorted, disjoint, inside [0, M*P), with even start and length");
+    // chunks of at most 254 columns (TMA boxes are at most 256 elements wide, rows 16-byte multiples)
+    for (int done = 0; done < len[r];) {
+      const int w = (len[r] - done) < 254 ? (len[r] - done) : 254;
+      ch_col0.push_back(col0[r] + done);
+      ch_w.push_back(w);
+      ch_off.push_back((int32_t)(total + done));
+      done += w;
+    }
+    total += len[r];
+    prev_end = col0[r] + len[r];
+  }
+  if (total != c.const_image_doubles) return fail(OPTY_ERR_ARG, "constant runs do not match cfg.const_image_doubles");
+  if ((int)ch_w.size() > OPTY_REPL_MAX_CHUNKS) return fail(OPTY_ERR_ARG, "too many constant-run chunks");
+  for (long long i = 0; i < total; ++i)
+    if (inv_idx[i] >= c.num_inv) return fail(OPTY_ERR_ARG, "invariant index out of range");
+  if (const char* e = getenv("OPTY_B200_REPL_MODE")) h->repl_mode = atoi(e);
+  if (const char* e = getenv("OPTY_B200_REPL_NODES")) h->repl_nodes_per_block = atoi(e);
+  if (h->repl_nodes_per_block < 1) return fail(OPTY_ERR_ARG, "invalid replicator geometry");
+  if ((size_t)c.const_image_doubles * 8 > 200u * 1024u)
+    return fail(OPTY_ERR_ARG, "constant-run image exceeds 200 KB of shared memory");
+  RT_CHECK(cudaFuncSetAttribute(opty_replicate_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  {
+    std::vector<int32_t> offs(num_runs);
+    int32_t acc = 0;
+    for (int r = 0; r < num_runs; ++r) {
+      offs[r] = acc;
+      acc += len[r];
+    }
+    cudaFree(h->d_run_col0);
+    cudaFree(h->d_run_len);
+    cudaFree(h->d_run_off);
+    h->d_run_col0 = h->d_run_len = h->d_run_off = nullptr;
+    RT_CHECK(cudaMalloc(&h->d_run_col0, (size_t)num_runs * 4));
+    RT_CHECK(cudaMalloc(&h->d_run_len, (size_t)num_runs * 4));
+    RT_CHECK(cudaMalloc(&h->d_run_off, (size_t)num_runs * 4));
+    RT_CHECK(cudaMemcpy(h->d_run_col0, col0, (size_t)num_runs * 4, cudaMemcpyHostToDevice));
+    RT_CHECK(cudaMemcpy(h->d_run_len, len, (size_t)num_runs * 4, cudaMemcpyHostToDevice));
+    RT_CHECK(cudaMemcpy(h->d_run_off, offs.data(), (size_t)num_runs * 4, cudaMemcpyHostToDevice));
+    h->repl_runs = num_runs;
+  }
+  if (const char* e = getenv("OPTY_B200_REPL_ROWS")) h->repl_rows = atoi(e);
+  if (const char* e = getenv("OPTY_B200_REPL_TILES")) h->repl_tiles_per_block = atoi(e);
+  if (h->repl_rows < 1 || h->repl_rows > 256 || h->repl_tiles_per_block < 1)
+    return fail(OPTY_ERR_ARG, "invalid replicator geometry");
+  int wmax = 0;
+  for (int w : ch_w) wmax = w > wmax ? w : wmax;
+  h->repl_smem = (size_t)h->repl_rows * wmax * 8;
+  if (h->repl_smem > 200u * 1024u) return fail(OPTY_ERR_ARG, "replicator image exceeds 200 KB of shared memory");
+  RT_CHECK(cudaFuncSetAttribute(opty_replicate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  cudaFree(h->d_repl_lit);
+  cudaFree(h->d_repl_inv);
+  cudaFree(h->d_repl_off);
+  cudaFree(h->d_repl_w);
+  h->d_repl_lit = nullptr;
+  h->d_repl_inv = h->d_repl_off = h->d_repl_w = nullptr;
+  const int nch = (int)ch_w.size();
+  RT_CHECK(cudaMalloc(&h->d_repl_lit, (size_t)total * 8));
+  RT_CHECK(cudaMalloc(&h->d_repl_inv, (size_t)total * 4));
+  RT_CHECK(cudaMalloc(&h->d_repl_off, (size_t)nch * 4));
+  RT_CHECK(cudaMalloc(&h->d_repl_w, (size_t)nch * 4));
+  RT_CHECK(cudaMemcpy(h->d_repl_lit, lit, (size_t)total * 8, cudaMemcpyHostToDevice));
+  RT_CHECK(cudaMemcpy(h->d_repl_inv, inv_idx, (size_t)total * 4, cudaMemcpyHostToDevice));
+  RT_CHECK(cudaMemcpy(h->d_repl_off, ch_off.data(), (size_t)nch * 4, cudaMemcpyHostToDevice));
+  RT_CHECK(cudaMemcpy(h->d_repl_w, ch_w.data(), (size_t)nch * 4, cudaMemcpyHostToDevice));
+  h->repl_maps.assign(c.out_ring, OptyReplMaps());
+  for (int s = 0; s < c.out_ring; ++s) {
+    memset(&h->repl_maps[s], 0, sizeof(OptyReplMaps));
+    for (int k = 0; k < nch; ++k) {
+      int rc = encode_2d(&h->repl_maps[s].m[k], h->d_jac[s] + ch_col0[k], (uint64_t)ch_w[k], (uint64_t)h->nn,
+                         (uint64_t)h->K * 8, (uint32_t)ch_w[k], (uint32_t)h->repl_rows);
+      if (rc) return rc;
+    }
+  }
+  h->repl_col0 = ch_col0;
+  h->repl_w = ch_w;
+  h->repl_off = ch_off;
+  h->repl_chunks = nch;
+  h->evaluated = false;
   return OPTY_OK;
 }
 

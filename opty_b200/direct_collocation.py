@@ -57,10 +57,18 @@ DEFAULT_CUDA_OPTIONS = {
                                 # like gcc -O2 on x86-64, residuals then match
                                 # the reference bit for bit in ~90 % of entries)
     'maxrregcount': None,
-    'tma_load': True,
+    'tma_load': True,           # input staging: True = TMA tile loads into
+                                # shared memory, False = plain loads into
+                                # shared memory, 'direct' = no staging
     'tma_store': True,
     'pre_pass': True,           # shared expensive sub-expressions once per node
+    'const_runs': False,        # node-invariant column runs are replicated by
+                                # a separate kernel (own stream) instead of
+                                # being staged per node by the group bodies;
+                                # measured: no gain at config 2 (profiles/)
+    'const_run_min': 16,        # shortest run (columns) worth carving out
     'debug_nostore': False,     # measurement aid: skip Jacobian tile stores
+    'debug_reps': 1,            # measurement aid: evaluate every tile n times
     'out_ring': 1,              # device output sets to rotate through
     'use_sympy_cse': True,
     'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
@@ -583,7 +591,10 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     M = prog.M
     K = M * prog.P
     tma_store = bool(opts['tma_store']) and K % 2 == 0
-    tma_load = bool(opts['tma_load']) and prog.R <= 256
+    if opts['tma_load'] == 'direct':
+        tma_load = 2
+    else:
+        tma_load = int(bool(opts['tma_load']) and prog.R <= 256)
     groups = opts['groups']
     if groups == 'auto':
         node_warps = -(-num_nodes // 32)
@@ -593,6 +604,10 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         groups = max(1, g_par, g_cost)
     groups = int(min(groups, M, runtime.OPTY_MAX_GROUPS))
     align = 2 if tma_store else 1
+    const_runs = []
+    if opts['const_runs'] and tma_store:
+        const_runs = prog.constant_runs(min_len=int(opts['const_run_min']))
+    prog.set_carved(const_runs)
     parts = prog.partition_rows(groups, col_align=align)
     derived = []
     if opts['pre_pass'] and len(parts) > 1:
@@ -601,8 +616,8 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
             # re-balance with the shared work taken out of the groups
             parts = prog.partition_rows(groups, col_align=align,
                                         stop=set(derived))
-    if prog.R + len(derived) > 256:
-        tma_load = False
+    if prog.R + len(derived) > 256 and tma_load == 1:
+        tma_load = 0
 
     logger.info('Emitting the CUDA module.')
     source, meta = codegen.emit_module(
@@ -612,7 +627,13 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         min_blocks_per_sm=opts['min_blocks_per_sm'],
         tma_load=tma_load, tma_store=tma_store, derived=derived,
         debug_nostore=opts['debug_nostore'],
-        tile_bufs=opts['tile_bufs'])
+        tile_bufs=opts['tile_bufs'], debug_reps=opts['debug_reps'],
+        const_runs=const_runs)
+    if len(meta['segments']) > runtime.OPTY_MAX_SEGMENTS:
+        raise ValueError('The module needs {} store segments, at most {} are '
+                         'supported; raise const_run_min.'.format(
+                             len(meta['segments']),
+                             runtime.OPTY_MAX_SEGMENTS))
     flags = build.module_flags(fmad=opts['fmad'],
                                maxrregcount=opts['maxrregcount'])
     logger.info('Compiling the constraint and Jacobian kernels.')
@@ -636,9 +657,11 @@ def fill_kernel_config(cfg, meta, opts):
     cfg.tma_store = int(meta['tma_store'])
     cfg.out_ring = int(opts['out_ring'])
     cfg.prefetch_jac = int(bool(opts.get('prefetch_jacobian', False)))
-    for g, gm in enumerate(meta['groups']):
-        cfg.group_col0[g] = gm['col0']
-        cfg.group_ncols[g] = gm['ncols']
+    cfg.num_segments = len(meta['segments'])
+    cfg.const_image_doubles = meta['const_image_doubles']
+    for sid, (col0, ncols) in enumerate(meta['segments']):
+        cfg.seg_col0[sid] = col0
+        cfg.seg_ncols[sid] = ncols
 
 
 class _PreparedModule(object):
@@ -704,6 +727,9 @@ class _CudaEvaluator(object):
         cfg.h = 0.0 if col._variable_duration else float(
             col.node_time_interval)
         self.handle = runtime.ColloHandle(cfg, cubin)
+        if meta['const_runs']:
+            self.handle.set_const_runs(meta['const_runs'], meta['const_lit'],
+                                       meta['const_inv'])
         self.nn = nn
         self.con_len = M * nn
         self.jac_len = nn * K

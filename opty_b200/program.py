@@ -213,8 +213,59 @@ class CollocationProgram(object):
 
     def row_costs(self):
         T = self.tape
-        return [T.cost(self.group_nodes([j])) + 2.0 * self.P
+        return [T.cost(self.group_nodes([j])) + 2.0 * self.row_store_cols(j)
                 for j in range(self.M)]
+
+    def row_store_cols(self, j):
+        """Jacobian columns of EOM row ``j`` that the group bodies store
+        (all ``P`` unless some were carved out as constant runs)."""
+        carved = getattr(self, 'carved', None)
+        if not carved:
+            return self.P
+        P = self.P
+        return P - sum(carved[j * P:(j + 1) * P])
+
+    def constant_runs(self, min_len=16, max_runs=32, max_doubles=24576):
+        """Maximal runs of consecutive Jacobian columns (of the flattened
+        ``M*P`` node block) whose entries are literals or node-invariant:
+        identical for every node, so one shared-memory image can be
+        replicated into all node rows by bulk copies instead of being
+        recomputed and staged per node.  Runs start at an even column and
+        have even length (16-byte alignment of TMA bulk copies).
+
+        Returns a list of ``(col0, length)`` sorted by column."""
+        kinds = self.entry_kind()
+        K = self.K
+        runs = []
+        c = 0
+        while c < K:
+            if kinds[c] == 2:
+                c += 1
+                continue
+            e = c
+            while e < K and kinds[e] != 2:
+                e += 1
+            a = c + (c & 1)
+            b = e - ((e - a) & 1)
+            if b - a >= min_len:
+                runs.append((a, b - a))
+            c = e
+        runs.sort(key=lambda r: -r[1])
+        keep = []
+        total = 0
+        for a, ln in runs:
+            if len(keep) >= max_runs or total + ln > max_doubles:
+                continue
+            keep.append((a, ln))
+            total += ln
+        return sorted(keep)
+
+    def set_carved(self, runs):
+        carved = [False] * self.K
+        for a, ln in runs:
+            for c in range(a, a + ln):
+                carved[c] = True
+        self.carved = carved if runs else None
 
     def partition_rows(self, num_groups, col_align=2, stop=None):
         """Splits the EOM rows into at most ``num_groups`` contiguous ranges
@@ -237,7 +288,8 @@ class CollocationProgram(object):
             c = cost_cache.get(key)
             if c is None:
                 c = (self.tape.cost(self.group_nodes(range(r0, r1), stop)) +
-                     2.0 * P * (r1 - r0))
+                     2.0 * sum(self.row_store_cols(j)
+                               for j in range(r0, r1)))
                 cost_cache[key] = c
             return c
 

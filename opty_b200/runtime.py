@@ -13,7 +13,8 @@ import numpy as np
 from . import build
 
 OPTY_MAX_GROUPS = 64
-ABI_VERSION = 2
+OPTY_MAX_SEGMENTS = 128
+ABI_VERSION = 3
 
 EXPORTS = (
     'opty_b200_abi_version', 'opty_colloc_create', 'opty_colloc_destroy',
@@ -21,6 +22,7 @@ EXPORTS = (
     'opty_colloc_eval_device', 'opty_colloc_constraints',
     'opty_colloc_jacobian', 'opty_colloc_host_buffers',
     'opty_colloc_device_buffers', 'opty_colloc_set_d2h_columns',
+    'opty_colloc_set_const_runs',
     'opty_colloc_last_kernel_ms', 'opty_colloc_time_device_evals',
     'opty_colloc_launch_count',
     'opty_colloc_jacobian_indices', 'opty_colloc_last_error',
@@ -56,8 +58,10 @@ class ColloCfg(ctypes.Structure):
         ('con_tail', ctypes.c_int32),
         ('jac_tail', ctypes.c_int32),
         ('prefetch_jac', ctypes.c_int32),
-        ('group_col0', ctypes.c_int32 * OPTY_MAX_GROUPS),
-        ('group_ncols', ctypes.c_int32 * OPTY_MAX_GROUPS),
+        ('num_segments', ctypes.c_int32),
+        ('const_image_doubles', ctypes.c_int32),
+        ('seg_col0', ctypes.c_int32 * OPTY_MAX_SEGMENTS),
+        ('seg_ncols', ctypes.c_int32 * OPTY_MAX_SEGMENTS),
         ('h', ctypes.c_double),
     ]
 
@@ -98,6 +102,8 @@ def load_library(path=None):
         ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]
     lib.opty_colloc_set_d2h_columns.argtypes = [c_vp, ctypes.c_int, c_vp,
                                                 c_vp, c_vp]
+    lib.opty_colloc_set_const_runs.argtypes = [c_vp, ctypes.c_int, c_vp, c_vp,
+                                               c_vp, c_vp]
     lib.opty_colloc_last_kernel_ms.argtypes = [c_vp,
                                                ctypes.POINTER(ctypes.c_float)]
     lib.opty_colloc_time_device_evals.argtypes = [
@@ -257,6 +263,19 @@ class ColloHandle(object):
         _check(self.lib, self.lib.opty_colloc_set_d2h_columns(
             self._h, n, ctypes.cast(b, ctypes.c_void_p),
             ctypes.cast(e, ctypes.c_void_p), fp))
+
+    def set_const_runs(self, runs, lit, inv_idx):
+        """``runs``: list of ``(col0, length)``; ``lit`` / ``inv_idx``: the
+        pattern of all runs concatenated."""
+        col0 = np.array([r[0] for r in runs], dtype=np.int32)
+        length = np.array([r[1] for r in runs], dtype=np.int32)
+        lit = np.ascontiguousarray(lit, dtype=np.float64)
+        inv_idx = np.ascontiguousarray(inv_idx, dtype=np.int32)
+        if len(lit) != int(length.sum()) or len(inv_idx) != len(lit):
+            raise ValueError('pattern length does not match the runs')
+        _check(self.lib, self.lib.opty_colloc_set_const_runs(
+            self._h, len(runs), col0.ctypes.data, length.ctypes.data,
+            lit.ctypes.data, inv_idx.ctypes.data))
 
     def last_kernel_ms(self):
         ms = ctypes.c_float()

@@ -61,6 +61,9 @@ def ufuncify_matrix(args, expr, const=None, tmp_dir=None, parallel=False,
             cfg.method = ELEMENTWISE
             cfg.h = 0.0
             h = runtime.ColloHandle(cfg, cubin)
+            if meta['const_runs']:
+                h.set_const_runs(meta['const_runs'], meta['const_lit'],
+                                 meta['const_inv'])
             h.set_known(None, None)
             handles[n] = h
         return h

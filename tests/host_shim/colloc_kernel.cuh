@@ -41,8 +41,8 @@ static inline double opty_sign(double x) { return (double)((x > 0.0) - (x < 0.0)
 #define OPTY_CON(j, val) ctx.con[(long long)(j) * ctx.ldc] = (val)
 #define OPTY_JS2(buf, tc, v0, v1) do { const_cast<OptyCtx&>(ctx).tile[buf][tc] = (v0); const_cast<OptyCtx&>(ctx).tile[buf][(tc) + 1] = (v1); } while (0)
 #define OPTY_JS1(buf, tc, v0) const_cast<OptyCtx&>(ctx).tile[buf][tc] = (v0)
-#define OPTY_FLUSH(g, q, col0, ncols) \
-  memcpy(ctx.jac + (long long)ctx.node * OPTY_K + (col0) + (q) * OPTY_C, ctx.tile[(q) % OPTY_NBUF], (ncols) * sizeof(double))
+#define OPTY_FLUSH(seg, q, buf, segcol0, ncols) \
+  memcpy(ctx.jac + (long long)ctx.node * OPTY_K + (segcol0) + (q) * OPTY_C, ctx.tile[buf], (ncols) * sizeof(double))
 #define OPTY_DRAIN() do { } while (0)
 #define OPTY_THREADS 1
 #define OPTY_PRE_THREADS 1
@@ -62,6 +62,7 @@ static inline double opty_sign(double x) { return (double)((x > 0.0) - (x < 0.0)
   const int opty_pg = (int)blockIdx.y;
 
 extern "C" void opty_colloc_inv(const double* uni, double* inv);
+extern "C" void host_get_invariants(double* out) { memcpy(out, opty_ci, sizeof(opty_ci)); }
 extern "C" void opty_colloc_pre(const OptyParams p);
 extern "C" void opty_colloc_eval(const OptyTmaps tm, const OptyParams p);
 
@@ -72,7 +73,7 @@ extern "C" void host_eval(const double* uni, double* traj, long long ldt, int n_
   opty_colloc_inv(uni, opty_ci);
   OptyTmaps tm; OptyParams p;
   p.traj = traj; p.con = con; p.jac = jac; p.ldt = ldt; p.ldc = n_nodes; p.n_nodes = n_nodes; p.n_cols = n_nodes + 1;
-  for (int pg = 0; pg < 64; ++pg)
+  for (int pg = 0; pg < 300; ++pg)
     for (int i = 0; i < n_nodes; ++i) { blockIdx.x = i; blockIdx.y = pg; opty_colloc_pre(p); }
   for (int g = 0; g < OPTY_NGROUPS; ++g)
     for (int i = 0; i < n_nodes; ++i) { blockIdx.x = i; blockIdx.y = g; opty_colloc_eval(tm, p); }

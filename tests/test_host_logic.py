@@ -379,7 +379,7 @@ def test_c_abi_library_exports_every_declared_symbol():
 def test_c_abi_config_struct_layout_matches_header():
     src = ('#include "opty_b200.h"\n#include <stdio.h>\n#include <stddef.h>\n'
            'int main(void){printf("%zu %zu %zu", sizeof(opty_colloc_cfg), '
-           'offsetof(opty_colloc_cfg, group_col0), '
+           'offsetof(opty_colloc_cfg, seg_col0), '
            'offsetof(opty_colloc_cfg, h)); return 0;}')
     with tempfile.TemporaryDirectory() as tmp:
         c = os.path.join(tmp, 'sz.c')
@@ -390,7 +390,7 @@ def test_c_abi_config_struct_layout_matches_header():
         out = subprocess.run([exe], capture_output=True, text=True).stdout
     size, off_g, off_h = (int(v) for v in out.split())
     assert size == ctypes.sizeof(runtime.ColloCfg)
-    assert off_g == runtime.ColloCfg.group_col0.offset
+    assert off_g == runtime.ColloCfg.seg_col0.offset
     assert off_h == runtime.ColloCfg.h.offset
 
 

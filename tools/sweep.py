@@ -25,6 +25,17 @@ def main():
     ref = None
     for name, opts in VARIANTS:
         opts = dict(opts)
+        for key in ('OPTY_B200_REPL_ROWS', 'OPTY_B200_REPL_TILES',
+                    'OPTY_B200_REPL_MODE', 'OPTY_B200_REPL_NODES'):
+            os.environ.pop(key, None)
+        for key, val in opts.pop('env', {}).items():
+            os.environ[key] = str(val)
+        cap = opts.pop('resident_blocks', None)
+        if cap:
+            os.environ['OPTY_B200_DEBUG_SMEM_FLOOR'] = str(
+                (227 * 1024) // cap - 1024)
+        else:
+            os.environ.pop('OPTY_B200_DEBUG_SMEM_FLOOR', None)
         opts.setdefault('out_ring', 4)
         col = ConstraintCollocator(*w.collocator_args(),
                                    **w.collocator_kwargs(), cuda_options=opts)
@@ -50,6 +61,9 @@ def main():
         if ref is None:
             ref = jac
         same = bool(np.array_equal(ref, jac))
+        if not same:
+            same = 'max|d|/max|ref|=%.2e' % (np.max(np.abs(ref - jac)) /
+                                               np.max(np.abs(ref)))
         B = 84551728
         print('%-34s %8.2f us  %7.1f GB/s  bit-equal-to-first=%s' % (
             name, 1e3 * min(ms), B / min(ms) / 1e6, same), flush=True)
