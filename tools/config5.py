@@ -23,6 +23,7 @@ import workloads  # noqa: E402
 from opty_b200 import ConstraintCollocator  # noqa: E402
 
 OPTS = {'prefetch_jacobian': False, 'd2h_skip_constants': False}
+OPTS.update(json.loads(os.environ.get('OPTY_OPTS', '{}')))
 N_FULL, N_CHECK = 50000, 2000
 
 
