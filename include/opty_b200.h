@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define OPTY_B200_ABI_VERSION 3
+#define OPTY_B200_ABI_VERSION 4
 #define OPTY_MAX_GROUPS 64
 #define OPTY_MAX_SEGMENTS 128
 
@@ -82,6 +82,8 @@ typedef struct opty_colloc_cfg {
   int32_t jac_tail;         /* extra host slots after the (N-1)*M*P partials */
   int32_t prefetch_jac;     /* opty_colloc_constraints starts the Jacobian D2H speculatively */
   int32_t num_segments;     /* store segments: column runs of the node block written by the group bodies */
+  int32_t primary_segments; /* segments [0, primary_segments) belong to the module given to
+                               opty_colloc_create; the rest to modules added with opty_colloc_add_module */
   int32_t const_image_doubles; /* total length of the constant column runs that the pre-pass kernel
                                   replicates into every node row (0: none); segments and constant
                                   runs together tile the M*P columns */
@@ -149,6 +151,16 @@ int opty_colloc_device_buffers(opty_colloc_t* h, void** traj, int64_t* ldt, void
  * full copies. */
 int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t* col_begin,
                                 const int32_t* col_end, const double* fill);
+
+/* Problems too large for one nvcc run are compiled as several modules (contiguous
+ * ranges of output groups) in parallel -- the reference compiles its single
+ * generated C function serially (opty/utils.py:866-907).  Adds the module that
+ * writes store segments [seg_first, seg_first + seg_count) with `num_groups`
+ * output groups; modules are added in segment order and all of them before the
+ * first evaluation.  The module given to opty_colloc_create carries the
+ * invariants and pre-pass kernels. */
+int opty_colloc_add_module(opty_colloc_t* h, const void* cubin, size_t cubin_bytes, int seg_first,
+                           int seg_count, int num_groups);
 
 /* Registers the constant column runs of the node block (cfg.const_image_doubles
  * columns in total): run i covers columns [col0[i], col0[i]+len[i]) (even start

@@ -181,14 +181,20 @@ def choose_tile_cols(requested):
 def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 min_blocks_per_sm=4, tma_load=True, tma_store=True,
                 derived=(), debug_nostore=False, tile_bufs=2, debug_reps=1,
-                const_runs=()):
+                const_runs=(), only_groups=None, with_aux=True):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(r0, r1)`` EOM row ranges).  ``derived`` lists the tape ids
     that the pre-pass kernel evaluates once per node into derived rows.
     ``const_runs`` lists ``(col0, length)`` column runs of the node block
     whose entries are the same for every node: the group bodies skip them
     and the runtime's replicator kernel copies one shared-memory image of
-    them into every node row with TMA tile stores."""
+    them into every node row with TMA tile stores.
+
+    Large problems are compiled as several modules in parallel: with
+    ``only_groups = (g0, g1)`` the module contains the bodies and the main
+    kernel of groups ``g0 .. g1-1`` only (group and store-segment indices
+    inside it are local); ``with_aux=False`` leaves out the invariants and
+    pre-pass kernels (the first module carries them)."""
     T = prog.tape
     M, P, K, R = prog.M, prog.P, prog.K, prog.R
     C = choose_tile_cols(tile_cols)
@@ -229,19 +235,23 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         for c in range(a, a + ln):
             seg_of_col[c] = sid
     ncc = sum(ln for _, ln in const_runs)
+    g0, g1 = only_groups if only_groups is not None else (0, len(groups))
+    seg_first = group_segments[g0][0] if group_segments[g0] else 0
+    local_segs = [sid for g in range(g0, g1) for sid in group_segments[g]]
+    assert local_segs == list(range(seg_first, seg_first + len(local_segs)))
 
     out = []
     w = out.append
     w('// generated by opty_b200.codegen (emitter v{}); do not edit'.format(
         EMITTER_VERSION))
-    w('#define OPTY_NSEGS {}'.format(max(len(segments), 1)))
+    w('#define OPTY_NSEGS {}'.format(max(len(local_segs), 1)))
     w('#define OPTY_M {}'.format(M))
     w('#define OPTY_P {}'.format(P))
     w('#define OPTY_K {}'.format(K))
     w('#define OPTY_R {}'.format(R))
     w('#define OPTY_D {}'.format(D))
     w('#define OPTY_C {}'.format(C))
-    w('#define OPTY_NGROUPS {}'.format(len(groups)))
+    w('#define OPTY_NGROUPS {}'.format(g1 - g0))
     w('#define OPTY_NINV {}'.format(max(ninv, 1)))
     w('#define OPTY_NUNI {}'.format(max(prog.num_uniform, 1)))
     w('#define OPTY_WARPS {}'.format(warps_per_block))
@@ -257,20 +267,22 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     w('')
 
     # ---- invariants kernel -------------------------------------------
-    bw = _BodyWriter(prog, 'inv')
-    for nid in prog.inv_nodes:
-        bw.need(nid)
-    w('extern "C" __global__ void opty_colloc_inv('
-      'const double* __restrict__ uni, double* __restrict__ inv)')
-    w('{')
-    w('  if (threadIdx.x != 0 || blockIdx.x != 0) return;')
-    for line in bw.lines:
-        w('  ' + line)
-    for k, nid in enumerate(prog.inv_nodes):
-        w('  inv[{}] = {};'.format(k, bw.ref(nid)))
-    w('}')
-    w('')
-    inv_ops = bw.num_ops
+    inv_ops = 0
+    if with_aux:
+        bw = _BodyWriter(prog, 'inv')
+        for nid in prog.inv_nodes:
+            bw.need(nid)
+        w('extern "C" __global__ void opty_colloc_inv('
+          'const double* __restrict__ uni, double* __restrict__ inv)')
+        w('{')
+        w('  if (threadIdx.x != 0 || blockIdx.x != 0) return;')
+        for line in bw.lines:
+            w('  ' + line)
+        for k, nid in enumerate(prog.inv_nodes):
+            w('  inv[{}] = {};'.format(k, bw.ref(nid)))
+        w('}')
+        w('')
+        inv_ops = bw.num_ops
 
     # ---- pre-pass kernel: derived rows, grid.y = groups of derived rows ---
     # rows that share their argument (sin / cos of the same angle) stay
@@ -296,30 +308,34 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 assert not T.varying[e]
                 const_lit.append(0.0)
                 const_inv.append(prog.inv_index[e])
-    w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
-    w('opty_colloc_pre(const OptyParams p)')
-    w('{')
-    w('  OPTY_PRE_BEGIN();')
-    w('  switch (opty_pg) {')
     pre_ops = 0
-    for pg, ks in enumerate(pre_chunks):
-        bw = _BodyWriter(prog, 'pre')
-        for k in ks:
-            bw.need(derived[k])
-            bw.lines.append('OPTY_DRV({}, {});'.format(k, bw.ref(derived[k])))
-        w('    case {}: {{'.format(pg))
-        for line in bw.lines:
-            w('      ' + line)
-        w('    } break;')
-        pre_ops += bw.num_ops
-    w('    default: break;')
-    w('  }')
-    w('}')
-    w('')
+    if with_aux:
+        w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
+        w('opty_colloc_pre(const OptyParams p)')
+        w('{')
+        w('  OPTY_PRE_BEGIN();')
+        w('  switch (opty_pg) {')
+        for pg, ks in enumerate(pre_chunks):
+            bw = _BodyWriter(prog, 'pre')
+            for k in ks:
+                bw.need(derived[k])
+                bw.lines.append('OPTY_DRV({}, {});'.format(
+                    k, bw.ref(derived[k])))
+            w('    case {}: {{'.format(pg))
+            for line in bw.lines:
+                w('      ' + line)
+            w('    } break;')
+            pre_ops += bw.num_ops
+        w('    default: break;')
+        w('  }')
+        w('}')
+        w('')
 
     # ---- group bodies --------------------------------------------------
     group_meta = []
     for g, (r0, r1) in enumerate(groups):
+        if not g0 <= g < g1:
+            continue
         bw = _BodyWriter(prog, 'main', derived_index)
         body = bw.lines
         w('static __device__ __forceinline__ void opty_group_{}('
@@ -334,8 +350,8 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
             ncols_in_chunk = cc % C or C
             q = (cc - 1) // C
             body.append('OPTY_FLUSH({}, {}, {}, {}, {});'.format(
-                sid, q, state['chunk'] % tile_bufs, segments[sid][0],
-                ncols_in_chunk))
+                sid - seg_first, q, state['chunk'] % tile_bufs,
+                segments[sid][0], ncols_in_chunk))
             state['chunk'] += 1
 
         def close_segment():
@@ -391,7 +407,7 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                            'ops': bw.num_ops, 'chunks': state['chunk']})
 
     # blockIdx.y -> group: most expensive groups are launched first
-    order = sorted(range(len(groups)),
+    order = sorted(range(len(group_meta)),
                    key=lambda g: -(20 * group_meta[g]['ops'] +
                                    43 * group_meta[g]['ncols']))
     w('__device__ const int opty_group_order[OPTY_NGROUPS] = {{{}}};'.format(
@@ -409,8 +425,8 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         w('#pragma unroll 1')
         w('  for (int opty_rep = 0; opty_rep < OPTY_DEBUG_REPS; ++opty_rep)')
     w('  switch (opty_g) {')
-    for g in range(len(groups)):
-        w('    case {}: opty_group_{}(ctx); break;'.format(g, g))
+    for g in range(g0, g1):
+        w('    case {}: opty_group_{}(ctx); break;'.format(g - g0, g))
     w('    default: break;')
     w('  }')
     w('  OPTY_KERNEL_END()')
@@ -420,8 +436,10 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     meta = {
         'emitter_version': EMITTER_VERSION,
         'M': M, 'P': P, 'K': K, 'R': R, 'C': C, 'D': D,
-        'num_groups': len(groups),
+        'num_groups': g1 - g0,
         'groups': group_meta,
+        'group_range': [g0, g1],
+        'segment_range': [seg_first, seg_first + len(local_segs)],
         'segments': [list(sg) for sg in segments],
         'const_runs': [list(cr) for cr in const_runs],
         'const_image_doubles': ncc,

@@ -285,6 +285,16 @@ struct opty_colloc {
   bool evaluated = false;
   bool con_fetched = false, jac_fetched = false;
 
+  // additional modules of a problem compiled in several pieces (groups beyond the primary module's)
+  struct ExtraModule {
+    CUmodule mod = nullptr;
+    CUfunction f_eval = nullptr;
+    CUdeviceptr ci_sym = 0;
+    int seg_first = 0, seg_count = 0, num_groups = 0;
+    std::vector<std::vector<unsigned char>> tmaps;  // per ring slot
+  };
+  std::vector<ExtraModule> extra;
+
   // constant-run replicator
   int repl_chunks = 0;                 // 0: no constant runs registered
   int repl_mode = 0;                   // 0: coalesced stores, 1: TMA tile stores
@@ -327,10 +337,15 @@ int encode_2d(CUtensorMap* map, void* base, uint64_t dim0, uint64_t dim1, uint64
   return OPTY_OK;
 }
 
+int build_tmaps_into(opty_colloc* h, int slot, int seg_first, int seg_count, std::vector<unsigned char>& blob);
+
 int build_tmaps(opty_colloc* h, int slot) {
+  return build_tmaps_into(h, slot, 0, h->cfg.primary_segments, h->tmaps[slot]);
+}
+
+int build_tmaps_into(opty_colloc* h, int slot, int seg_first, int seg_count, std::vector<unsigned char>& blob) {
   const opty_colloc_cfg& c = h->cfg;
-  std::vector<unsigned char>& blob = h->tmaps[slot];
-  blob.assign(sizeof(CUtensorMap) * (1 + (c.num_segments > 0 ? c.num_segments : 1)), 0);
+  blob.assign(sizeof(CUtensorMap) * (1 + (seg_count > 0 ? seg_count : 1)), 0);
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(blob.data());
   int rc;
   if (c.tma_load == 1) {
@@ -341,9 +356,10 @@ int build_tmaps(opty_colloc* h, int slot) {
       return rc;
   }
   if (c.tma_store) {
-    for (int g = 0; g < c.num_segments; ++g) {
-      if ((rc = encode_2d(&maps[1 + g], h->d_jac[slot] + c.seg_col0[g], (uint64_t)c.seg_ncols[g],
-                          (uint64_t)h->nn, (uint64_t)h->K * 8, (uint32_t)c.tile_cols, 32u)))
+    for (int g = 0; g < seg_count; ++g) {
+      if ((rc = encode_2d(&maps[1 + g], h->d_jac[slot] + c.seg_col0[seg_first + g],
+                          (uint64_t)c.seg_ncols[seg_first + g], (uint64_t)h->nn, (uint64_t)h->K * 8,
+                          (uint32_t)c.tile_cols, 32u)))
         return rc;
     }
   }
@@ -367,6 +383,15 @@ int launch_eval(opty_colloc* h) {
     h->launches++;
     RT_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(h->ci_sym), h->d_inv, (size_t)c.num_inv * 8,
                              cudaMemcpyDeviceToDevice, h->stream));
+    for (auto& em : h->extra)
+      RT_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(em.ci_sym), h->d_inv, (size_t)c.num_inv * 8,
+                               cudaMemcpyDeviceToDevice, h->stream));
+  }
+  {
+    int covered = c.primary_segments;
+    for (auto& em : h->extra) covered += em.seg_count;
+    if (covered != c.num_segments)
+      return fail(OPTY_ERR_STATE, "not all modules of this problem have been added (opty_colloc_add_module)");
   }
   h->inv_dirty = false;
   h->ring = (h->ring + 1) % c.out_ring;
@@ -412,6 +437,12 @@ int launch_eval(opty_colloc* h) {
   DRV_CHECK(g_drv.LaunchKernel(h->f_eval, h->grid_x, (unsigned)c.num_groups, 1, 32u * c.warps_per_block, 1, 1, h->smem_bytes,
                                (CUstream)h->stream, args, nullptr));
   h->launches++;
+  for (auto& em : h->extra) {
+    void* eargs[2] = {em.tmaps[h->ring].data(), &p};
+    DRV_CHECK(g_drv.LaunchKernel(em.f_eval, h->grid_x, (unsigned)em.num_groups, 1, 32u * c.warps_per_block, 1, 1,
+                                 h->smem_bytes, (CUstream)h->stream, eargs, nullptr));
+    h->launches++;
+  }
   if (c.const_image_doubles > 0) RT_CHECK(cudaStreamWaitEvent(h->stream, h->ev_repl_done, 0));
   RT_CHECK(cudaEventRecord(h->ev1, h->stream));
   h->have_ms = true;
@@ -458,14 +489,33 @@ int enqueue_jac_copy(opty_colloc* h, cudaStream_t st) {
 
 int upload(opty_colloc* h, const double* free_host, bool* changed_out) {
   const opty_colloc_cfg& c = h->cfg;
-  const size_t bytes = h->free_len * 8;
+  const int nrows = c.n + c.q;
   // IPOPT evaluates g and jac_g at the same point back to back: compare with
   // the staged copy (a vector handed over in the pinned buffer itself cannot
-  // be compared and always counts as new)
-  const bool changed = !h->free_valid || free_host == h->h_free || memcmp(free_host, h->h_free, bytes) != 0;
+  // be compared and always counts as new).  Only the part of the free vector
+  // this handle evaluates is compared and staged: its column window of every
+  // trajectory row plus the parameter / time-interval tail, so a shard's host
+  // work does not grow with the size of the whole problem.
+  const size_t win_bytes = (size_t)h->ncols * 8;
+  const size_t tail_off = (size_t)nrows * c.N;
+  const size_t tail_bytes = (size_t)(c.r + c.s) * 8;
+  bool changed = !h->free_valid || free_host == h->h_free;
+  if (!changed) {
+    for (int r = 0; r < nrows && !changed; ++r) {
+      const size_t off = (size_t)r * c.N + c.node_lo;
+      changed = memcmp(free_host + off, h->h_free + off, win_bytes) != 0;
+    }
+    if (!changed && tail_bytes) changed = memcmp(free_host + tail_off, h->h_free + tail_off, tail_bytes) != 0;
+  }
   if (changed_out) *changed_out = changed;
   if (!changed) return OPTY_OK;
-  if (free_host != h->h_free) memcpy(h->h_free, free_host, bytes);
+  if (free_host != h->h_free) {
+    for (int r = 0; r < nrows; ++r) {
+      const size_t off = (size_t)r * c.N + c.node_lo;
+      memcpy(h->h_free + off, free_host + off, win_bytes);
+    }
+    if (tail_bytes) memcpy(h->h_free + tail_off, free_host + tail_off, tail_bytes);
+  }
   const int rows = c.n + c.q;
   // rows of the free vector are [row][N]; this handle keeps columns node_lo..node_hi
   RT_CHECK(cudaMemcpy2DAsync(h->d_traj, (size_t)h->ldt * 8, h->h_free + c.node_lo, (size_t)c.N * 8,
@@ -513,7 +563,8 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   if (!elementwise && cfg->P != expectP)
     return fail(OPTY_ERR_ARG, "P does not match n, q, r, s and the integration method");
   {
-    if (cfg->num_segments < 0 || cfg->num_segments > OPTY_MAX_SEGMENTS || cfg->const_image_doubles < 0)
+    if (cfg->num_segments < 0 || cfg->num_segments > OPTY_MAX_SEGMENTS || cfg->const_image_doubles < 0 ||
+        cfg->primary_segments < 0 || cfg->primary_segments > cfg->num_segments)
       return fail(OPTY_ERR_ARG, "invalid segment count");
     long long covered = cfg->const_image_doubles, prev_end = 0;
     for (int g = 0; g < cfg->num_segments; ++g) {
@@ -669,6 +720,8 @@ int opty_colloc_destroy(opty_colloc_t* h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(h->mod);
+  for (auto& em : h->extra)
+    if (em.mod && g_drv.ModuleUnload) g_drv.ModuleUnload(em.mod);
   delete h;
   return OPTY_OK;
 }
@@ -816,6 +869,47 @@ int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t*
   h->d2h_end.swap(e);
   h->jac_fetched = false;
   if (!fill) h->full_fetch[0] = h->full_fetch[1] = true;
+  return OPTY_OK;
+}
+
+int opty_colloc_add_module(opty_colloc_t* h, const void* cubin, size_t cubin_bytes, int seg_first, int seg_count,
+                           int num_groups) {
+  if (!h || !cubin || cubin_bytes == 0) return fail(OPTY_ERR_ARG, "null argument");
+  const opty_colloc_cfg& c = h->cfg;
+  int expect_first = c.primary_segments;
+  for (auto& em : h->extra) expect_first += em.seg_count;
+  if (seg_first != expect_first || seg_count < 0 || seg_first + seg_count > c.num_segments || num_groups < 1 ||
+      num_groups > OPTY_MAX_GROUPS)
+    return fail(OPTY_ERR_ARG, "modules must be added in segment order and stay inside cfg.num_segments");
+  RT_CHECK(cudaSetDevice(c.device));
+  opty_colloc::ExtraModule em;
+  em.seg_first = seg_first;
+  em.seg_count = seg_count;
+  em.num_groups = num_groups;
+  DRV_CHECK(g_drv.ModuleLoadData(&em.mod, cubin));
+  CUresult r1 = g_drv.ModuleGetFunction(&em.f_eval, em.mod, "opty_colloc_eval");
+  size_t ci_bytes = 0;
+  CUresult r2 = r1 == CUDA_SUCCESS ? g_drv.ModuleGetGlobal(&em.ci_sym, &ci_bytes, em.mod, "opty_ci") : r1;
+  CUresult r3 = r2 == CUDA_SUCCESS ? g_drv.FuncSetAttribute(em.f_eval, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                                            (int)h->smem_bytes)
+                                   : r2;
+  if (r3 != CUDA_SUCCESS || ci_bytes < (size_t)c.num_inv * 8) {
+    g_drv.ModuleUnload(em.mod);
+    return fail(r3 != CUDA_SUCCESS ? OPTY_ERR_CUDA : OPTY_ERR_ARG,
+                r3 != CUDA_SUCCESS ? "opty_colloc_add_module: " + drv_err(r3)
+                                   : std::string("module's invariant table is smaller than cfg.num_inv"));
+  }
+  em.tmaps.resize(c.out_ring);
+  for (int s = 0; s < c.out_ring; ++s) {
+    int rc = build_tmaps_into(h, s, seg_first, seg_count, em.tmaps[s]);
+    if (rc) {
+      g_drv.ModuleUnload(em.mod);
+      return rc;
+    }
+  }
+  h->extra.push_back(std::move(em));
+  h->inv_dirty = true;
+  h->evaluated = false;
   return OPTY_OK;
 }
 

@@ -73,6 +73,7 @@ DEFAULT_CUDA_OPTIONS = {
     'use_sympy_cse': True,
     'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
     'prefetch_jacobian': True,  # constraints() starts the Jacobian D2H early
+    'compile_shards': 'auto',   # modules compiled in parallel (large problems)
     'target_warps': 148 * 16,
     'max_group_cost': 6000.0,
 }
@@ -618,10 +619,22 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
                                         stop=set(derived))
     if prog.R + len(derived) > 256 and tma_load == 1:
         tma_load = 0
+    if tma_load != 2:
+        # staged input must fit beside the Jacobian tiles in 227 KB of shared
+        # memory per block; otherwise the lanes read the trajectory matrix
+        # directly (coalesced, read-only path)
+        threads = 32 * int(opts['warps_per_block'])
+        xseg = min(threads, 128)
+        xin = (threads // xseg) * (
+            -(-((prog.R + len(derived)) * (xseg + 2) * 8) // 128) * 128)
+        tiles = (int(opts['warps_per_block']) * int(opts['tile_bufs']) * 32 *
+                 codegen.choose_tile_cols(opts['tile_cols']) * 8)
+        if xin + tiles + 128 > 227 * 1024:
+            tma_load = 2
 
-    logger.info('Emitting the CUDA module.')
-    source, meta = codegen.emit_module(
-        prog, parts, method,
+    flags = build.module_flags(fmad=opts['fmad'],
+                               maxrregcount=opts['maxrregcount'])
+    emit_kwargs = dict(
         tile_cols=opts['tile_cols'],
         warps_per_block=opts['warps_per_block'],
         min_blocks_per_sm=opts['min_blocks_per_sm'],
@@ -629,18 +642,82 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         debug_nostore=opts['debug_nostore'],
         tile_bufs=opts['tile_bufs'], debug_reps=opts['debug_reps'],
         const_runs=const_runs)
+
+    # Large problems are split into several modules (contiguous ranges of
+    # output groups) that nvcc compiles in parallel; the runtime launches one
+    # main kernel per module.  The reference compiles its one generated C
+    # function serially (opty/utils.py:866-907); at the 50-link chain that is
+    # the dominant set-up cost.
+    shards = opts['compile_shards']
+    if shards == 'auto':
+        big = prog.stats()['varying_cost'] >= 40000 and len(parts) >= 4
+        shards = min(len(parts), os.cpu_count() or 1, 16) if big else 1
+    shards = max(1, min(int(shards), len(parts)))
+    if shards == 1:
+        ranges = [None]
+    else:
+        # contiguous chunks of groups with balanced cost
+        costs = [prog.tape.cost(prog.group_nodes(range(r0, r1),
+                                                 set(derived) or None))
+                 for r0, r1 in parts]
+        total = float(sum(costs)) or 1.0
+        cuts, acc = [], 0.0
+        for g, c in enumerate(costs[:-1]):
+            acc += c
+            # cut after group g once the running cost passes the next target,
+            # keeping enough groups for the remaining chunks
+            if len(cuts) < shards - 1 and \
+                    (acc >= total * (len(cuts) + 1) / shards or
+                     len(parts) - (g + 1) == shards - 1 - len(cuts)):
+                cuts.append(g + 1)
+        bounds = [0] + cuts + [len(parts)]
+        ranges = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+
+    logger.info('Emitting the CUDA module%s.',
+                '' if len(ranges) == 1 else 's ({})'.format(len(ranges)))
+    emitted = []
+    for i, rng in enumerate(ranges):
+        emitted.append(codegen.emit_module(
+            prog, parts, method, only_groups=rng, with_aux=(i == 0),
+            **emit_kwargs))
+    source, meta = emitted[0]
     if len(meta['segments']) > runtime.OPTY_MAX_SEGMENTS:
         raise ValueError('The module needs {} store segments, at most {} are '
                          'supported; raise const_run_min.'.format(
                              len(meta['segments']),
                              runtime.OPTY_MAX_SEGMENTS))
-    flags = build.module_flags(fmad=opts['fmad'],
-                               maxrregcount=opts['maxrregcount'])
     logger.info('Compiling the constraint and Jacobian kernels.')
-    cubin, cubin_path, cache_hit = build.compile_module(
-        source, flags, cache_dir=tmp_dir,
-        show_compile_output=show_compile_output)
+
+    def compile_one(src):
+        return build.compile_module(src, flags, cache_dir=tmp_dir,
+                                    show_compile_output=show_compile_output)
+
+    if len(emitted) == 1:
+        compiled = [compile_one(source)]
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(emitted),
+                                                os.cpu_count() or 1)) as ex:
+            compiled = list(ex.map(compile_one, [e[0] for e in emitted]))
+    cubin, cubin_path, cache_hit = compiled[0]
+    cache_hit = all(c[2] for c in compiled)
+    meta['extra_modules'] = [
+        {'cubin_path': c[1], 'group_range': e[1]['group_range'],
+         'segment_range': e[1]['segment_range'],
+         'num_groups': e[1]['num_groups'],
+         'groups': e[1]['groups']}
+        for e, c in zip(emitted[1:], compiled[1:])]
     return parts, derived, source, meta, cubin, cubin_path, cache_hit
+
+
+def attach_extra_modules(handle, meta):
+    """Loads the additional modules of a problem that was compiled in
+    several pieces into ``handle``."""
+    for em in meta.get('extra_modules', ()):
+        with open(em['cubin_path'], 'rb') as f:
+            cubin = f.read()
+        s0, s1 = em['segment_range']
+        handle.add_module(cubin, s0, s1 - s0, em['num_groups'])
 
 
 def fill_kernel_config(cfg, meta, opts):
@@ -658,6 +735,8 @@ def fill_kernel_config(cfg, meta, opts):
     cfg.out_ring = int(opts['out_ring'])
     cfg.prefetch_jac = int(bool(opts.get('prefetch_jacobian', False)))
     cfg.num_segments = len(meta['segments'])
+    seg_range = meta.get('segment_range', [0, len(meta['segments'])])
+    cfg.primary_segments = seg_range[1] - seg_range[0]
     cfg.const_image_doubles = meta['const_image_doubles']
     for sid, (col0, ncols) in enumerate(meta['segments']):
         cfg.seg_col0[sid] = col0
@@ -727,6 +806,7 @@ class _CudaEvaluator(object):
         cfg.h = 0.0 if col._variable_duration else float(
             col.node_time_interval)
         self.handle = runtime.ColloHandle(cfg, cubin)
+        attach_extra_modules(self.handle, meta)
         if meta['const_runs']:
             self.handle.set_const_runs(meta['const_runs'], meta['const_lit'],
                                        meta['const_inv'])

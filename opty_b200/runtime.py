@@ -14,7 +14,7 @@ from . import build
 
 OPTY_MAX_GROUPS = 64
 OPTY_MAX_SEGMENTS = 128
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = (
     'opty_b200_abi_version', 'opty_colloc_create', 'opty_colloc_destroy',
@@ -22,7 +22,7 @@ EXPORTS = (
     'opty_colloc_eval_device', 'opty_colloc_constraints',
     'opty_colloc_jacobian', 'opty_colloc_host_buffers',
     'opty_colloc_device_buffers', 'opty_colloc_set_d2h_columns',
-    'opty_colloc_set_const_runs',
+    'opty_colloc_set_const_runs', 'opty_colloc_add_module',
     'opty_colloc_last_kernel_ms', 'opty_colloc_time_device_evals',
     'opty_colloc_launch_count',
     'opty_colloc_jacobian_indices', 'opty_colloc_last_error',
@@ -59,6 +59,7 @@ class ColloCfg(ctypes.Structure):
         ('jac_tail', ctypes.c_int32),
         ('prefetch_jac', ctypes.c_int32),
         ('num_segments', ctypes.c_int32),
+        ('primary_segments', ctypes.c_int32),
         ('const_image_doubles', ctypes.c_int32),
         ('seg_col0', ctypes.c_int32 * OPTY_MAX_SEGMENTS),
         ('seg_ncols', ctypes.c_int32 * OPTY_MAX_SEGMENTS),
@@ -102,6 +103,9 @@ def load_library(path=None):
         ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]
     lib.opty_colloc_set_d2h_columns.argtypes = [c_vp, ctypes.c_int, c_vp,
                                                 c_vp, c_vp]
+    lib.opty_colloc_add_module.argtypes = [c_vp, c_vp, ctypes.c_size_t,
+                                           ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int]
     lib.opty_colloc_set_const_runs.argtypes = [c_vp, ctypes.c_int, c_vp, c_vp,
                                                c_vp, c_vp]
     lib.opty_colloc_last_kernel_ms.argtypes = [c_vp,
@@ -263,6 +267,13 @@ class ColloHandle(object):
         _check(self.lib, self.lib.opty_colloc_set_d2h_columns(
             self._h, n, ctypes.cast(b, ctypes.c_void_p),
             ctypes.cast(e, ctypes.c_void_p), fp))
+
+    def add_module(self, cubin, seg_first, seg_count, num_groups):
+        buf = ctypes.create_string_buffer(cubin, len(cubin))
+        self._extra_cubins = getattr(self, '_extra_cubins', []) + [buf]
+        _check(self.lib, self.lib.opty_colloc_add_module(
+            self._h, ctypes.cast(buf, ctypes.c_void_p), len(cubin),
+            int(seg_first), int(seg_count), int(num_groups)))
 
     def set_const_runs(self, runs, lit, inv_idx):
         """``runs``: list of ``(col0, length)``; ``lit`` / ``inv_idx``: the

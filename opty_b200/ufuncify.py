@@ -20,7 +20,8 @@ import numpy as np
 
 from . import runtime
 from .direct_collocation import (DEFAULT_CUDA_OPTIONS, fill_kernel_config,
-                                 prepare_program_module)
+                                 prepare_program_module,
+                                 attach_extra_modules)
 from .program import CollocationProgram
 
 ELEMENTWISE = 2
@@ -61,6 +62,7 @@ def ufuncify_matrix(args, expr, const=None, tmp_dir=None, parallel=False,
             cfg.method = ELEMENTWISE
             cfg.h = 0.0
             h = runtime.ColloHandle(cfg, cubin)
+            attach_extra_modules(h, meta)
             if meta['const_runs']:
                 h.set_const_runs(meta['const_runs'], meta['const_lit'],
                                  meta['const_inv'])

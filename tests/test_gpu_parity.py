@@ -214,6 +214,15 @@ def test_config2_kernel_variants_agree_bitwise(config2):
          'tile_bufs': 3, 'min_blocks_per_sm': 3},
         {'pre_pass': False, 'groups': 8, 'warps_per_block': 1,
          'min_blocks_per_sm': 8},
+        # constant column runs replicated by the runtime kernel, store
+        # segments, direct input loads, one staging tile per warp
+        {'const_runs': True, 'groups': 8, 'tma_load': 'direct',
+         'tile_cols': 46, 'tile_bufs': 1, 'warps_per_block': 1,
+         'min_blocks_per_sm': 8},
+        {'const_runs': True, 'const_run_min': 2, 'groups': 4,
+         'out_ring': 2},
+        # the problem compiled as three modules (parallel nvcc runs)
+        {'compile_shards': 3, 'groups': 8, 'out_ring': 2},
     ]
     ref_con = ref_jac = None
     for opts in variants:
