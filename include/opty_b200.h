@@ -35,9 +35,9 @@
 extern "C" {
 #endif
 
-#define OPTY_B200_ABI_VERSION 4
-#define OPTY_MAX_GROUPS 64
-#define OPTY_MAX_SEGMENTS 128
+#define OPTY_B200_ABI_VERSION 5
+#define OPTY_MAX_GROUPS 1024
+#define OPTY_MAX_SEGMENTS 1024
 
 #define OPTY_OK 0
 #define OPTY_ERR_ARG -1     /* invalid argument / configuration */

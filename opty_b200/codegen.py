@@ -183,7 +183,8 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 derived=(), debug_nostore=False, tile_bufs=2, debug_reps=1,
                 const_runs=(), only_groups=None, with_aux=True):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
-    (list of ``(r0, r1)`` EOM row ranges).  ``derived`` lists the tape ids
+    (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block;
+    a group also owns the residuals of the rows that start inside it).  ``derived`` lists the tape ids
     that the pre-pass kernel evaluates once per node into derived rows.
     ``const_runs`` lists ``(col0, length)`` column runs of the node block
     whose entries are the same for every node: the group bodies skip them
@@ -215,10 +216,10 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     # each gets its own TMA descriptor (box C x 32, clipped at the segment end)
     segments = []          # (col0, ncols)
     group_segments = []    # per group: list of segment ids
-    for (r0, r1) in groups:
+    for (gc0, gc1) in groups:
         ids = []
-        c = r0 * P
-        end = r1 * P
+        c = gc0
+        end = gc1
         while c < end:
             if carved[c]:
                 c += 1
@@ -333,7 +334,7 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
 
     # ---- group bodies --------------------------------------------------
     group_meta = []
-    for g, (r0, r1) in enumerate(groups):
+    for g, (gc0, gc1) in enumerate(groups):
         if not g0 <= g < g1:
             continue
         bw = _BodyWriter(prog, 'main', derived_index)
@@ -361,47 +362,47 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
             state['seg'] = None
             state['cc'] = 0
 
-        for j in range(r0, r1):
-            if prog.con:
+        for col in range(gc0, gc1):
+            j, k = divmod(col, P)
+            if k == 0 and prog.con:
                 bw.need(prog.con[j])
                 body.append('OPTY_CON({}, {});'.format(
                     j, bw.ref(prog.con[j])))
-            for k in range(P):
-                col = j * P + k
-                if carved[col]:
-                    continue
-                sid = seg_of_col[col]
-                if sid != state['seg']:
-                    close_segment()
-                    state['seg'] = sid
-                seg_ncols = segments[sid][1]
-                e = prog.jac[j][k]
-                bw.need(e)
-                cc = state['cc']
-                tc = cc % C
-                buf = state['chunk'] % tile_bufs
-                pending = state['pending']
-                if pending is None and tc % 2 == 0 and tc + 1 < C and \
-                        cc + 1 < seg_ncols:
-                    state['pending'] = (tc, bw.ref(e))
-                elif pending is not None:
-                    body.append('OPTY_JS2({}, {}, {}, {});'.format(
-                        buf, pending[0], pending[1], bw.ref(e)))
-                    state['pending'] = None
-                else:
-                    body.append('OPTY_JS1({}, {}, {});'.format(
-                        buf, tc, bw.ref(e)))
-                state['cc'] = cc + 1
-                state['stored'] += 1
-                if state['cc'] % C == 0 and state['pending'] is None:
-                    flush()
+            if carved[col]:
+                continue
+            sid = seg_of_col[col]
+            if sid != state['seg']:
+                close_segment()
+                state['seg'] = sid
+            seg_ncols = segments[sid][1]
+            e = prog.jac[j][k]
+            bw.need(e)
+            cc = state['cc']
+            tc = cc % C
+            buf = state['chunk'] % tile_bufs
+            pending = state['pending']
+            if pending is None and tc % 2 == 0 and tc + 1 < C and \
+                    cc + 1 < seg_ncols:
+                state['pending'] = (tc, bw.ref(e))
+            elif pending is not None:
+                body.append('OPTY_JS2({}, {}, {}, {});'.format(
+                    buf, pending[0], pending[1], bw.ref(e)))
+                state['pending'] = None
+            else:
+                body.append('OPTY_JS1({}, {}, {});'.format(
+                    buf, tc, bw.ref(e)))
+            state['cc'] = cc + 1
+            state['stored'] += 1
+            if state['cc'] % C == 0 and state['pending'] is None:
+                flush()
         close_segment()
         body.append('OPTY_DRAIN();')
         for line in body:
             w('  ' + line)
         w('}')
         w('')
-        group_meta.append({'rows': [r0, r1], 'col0': r0 * P,
+        group_meta.append({'rows': [gc0 // P, -(-gc1 // P)],
+                           'cols': [gc0, gc1], 'col0': gc0,
                            'ncols': state['stored'],
                            'segments': group_segments[g],
                            'ops': bw.num_ops, 'chunks': state['chunk']})

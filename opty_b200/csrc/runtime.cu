@@ -549,6 +549,8 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   if (cfg->node_lo < 0 || cfg->node_hi > cfg->N - (elementwise ? 0 : 1) || cfg->node_lo >= cfg->node_hi)
     return fail(OPTY_ERR_ARG, "invalid node range");
   if (cfg->num_groups < 1 || cfg->num_groups > OPTY_MAX_GROUPS) return fail(OPTY_ERR_ARG, "invalid group count");
+  if (cfg->primary_segments > 240)
+    return fail(OPTY_ERR_ARG, "a module's TMA descriptors are one kernel parameter: at most 240 store segments per module");
   if (cfg->warps_per_block < 1 || cfg->warps_per_block > 32 ||
       (cfg->warps_per_block > 4 && cfg->warps_per_block % 4 != 0) || cfg->tile_cols < 2 || (cfg->tile_cols & 1) ||
       cfg->tile_cols > 256)
@@ -879,8 +881,8 @@ int opty_colloc_add_module(opty_colloc_t* h, const void* cubin, size_t cubin_byt
   int expect_first = c.primary_segments;
   for (auto& em : h->extra) expect_first += em.seg_count;
   if (seg_first != expect_first || seg_count < 0 || seg_first + seg_count > c.num_segments || num_groups < 1 ||
-      num_groups > OPTY_MAX_GROUPS)
-    return fail(OPTY_ERR_ARG, "modules must be added in segment order and stay inside cfg.num_segments");
+      num_groups > OPTY_MAX_GROUPS || seg_count > 240)
+    return fail(OPTY_ERR_ARG, "modules must be added in segment order, stay inside cfg.num_segments and hold at most 240 segments");
   RT_CHECK(cudaSetDevice(c.device));
   opty_colloc::ExtraModule em;
   em.seg_first = seg_first;

@@ -51,8 +51,11 @@ DEFAULT_CUDA_OPTIONS = {
     'groups': 'auto',           # number of output groups (grid.y) or 'auto'
     'tile_cols': 30,            # Jacobian staging tile width (doubles)
     'tile_bufs': 2,             # staging tiles per warp (2..4)
-    'warps_per_block': 2,
-    'min_blocks_per_sm': 4,
+    'warps_per_block': 'auto',  # 2, or 8 when there are enough node tiles x
+                                # groups for >= 6 waves of 8-warp blocks (the
+                                # warps of a block share every instruction
+                                # fetch: large models are bound by that)
+    'min_blocks_per_sm': 'auto',  # 4 for 2-warp blocks, 1 for 8-warp blocks
     'fmad': True,               # FMA contraction (False: mul/add stay unfused
                                 # like gcc -O2 on x86-64, residuals then match
                                 # the reference bit for bit in ~90 % of entries)
@@ -73,6 +76,12 @@ DEFAULT_CUDA_OPTIONS = {
     'use_sympy_cse': True,
     'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
     'prefetch_jacobian': True,  # constraints() starts the Jacobian D2H early
+    'max_body_cost': 0.0,       # > 0: equations whose body would cost more
+                                # are cut into column blocks.  Off by default:
+                                # at the n-link chains the first block of an
+                                # equation (residual + d/dq_j) carries 80 % of
+                                # its operations, so the largest body hardly
+                                # shrinks while the total work doubles
     'compile_shards': 'auto',   # modules compiled in parallel (large problems)
     'target_warps': 148 * 16,
     'max_group_cost': 6000.0,
@@ -609,25 +618,51 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     if opts['const_runs'] and tma_store:
         const_runs = prog.constant_runs(min_len=int(opts['const_run_min']))
     prog.set_carved(const_runs)
-    parts = prog.partition_rows(groups, col_align=align)
+    P = prog.P
+    max_body = float(opts['max_body_cost'])
+    min_cols = 16 if align == 2 else 15
+
+    def column_parts(stop=None):
+        # balanced ranges of whole equations, then equations whose body
+        # would be too large are cut into column blocks
+        rows = prog.partition_rows(groups, col_align=align, stop=stop)
+        cparts = [(r0 * P, r1 * P) for r0, r1 in rows]
+        if max_body > 0 and tma_store:
+            cparts = prog.split_heavy(cparts, max_body, col_align=align,
+                                      min_cols=min_cols, stop=stop)
+        return cparts
+
+    parts = column_parts()
     derived = []
     if opts['pre_pass'] and len(parts) > 1:
         derived = prog.select_derived(parts, max_rows=max(0, 256 - prog.R))
         if derived:
             # re-balance with the shared work taken out of the groups
-            parts = prog.partition_rows(groups, col_align=align,
-                                        stop=set(derived))
+            parts = column_parts(stop=set(derived))
+    if len(parts) > runtime.OPTY_MAX_GROUPS:
+        raise ValueError('The problem needs {} output groups, at most {} are '
+                         'supported; raise max_body_cost.'.format(
+                             len(parts), runtime.OPTY_MAX_GROUPS))
     if prog.R + len(derived) > 256 and tma_load == 1:
         tma_load = 0
+    wpb = opts['warps_per_block']
+    if wpb == 'auto':
+        node_warps = -(-num_nodes // 32)
+        wpb = 8 if node_warps * len(parts) >= 8 * 148 * 6 else 2
+    wpb = int(wpb)
+    mbs = opts['min_blocks_per_sm']
+    if mbs == 'auto':
+        mbs = max(1, 8 // wpb)
+    mbs = int(mbs)
     if tma_load != 2:
         # staged input must fit beside the Jacobian tiles in 227 KB of shared
         # memory per block; otherwise the lanes read the trajectory matrix
         # directly (coalesced, read-only path)
-        threads = 32 * int(opts['warps_per_block'])
+        threads = 32 * wpb
         xseg = min(threads, 128)
         xin = (threads // xseg) * (
             -(-((prog.R + len(derived)) * (xseg + 2) * 8) // 128) * 128)
-        tiles = (int(opts['warps_per_block']) * int(opts['tile_bufs']) * 32 *
+        tiles = (wpb * int(opts['tile_bufs']) * 32 *
                  codegen.choose_tile_cols(opts['tile_cols']) * 8)
         if xin + tiles + 128 > 227 * 1024:
             tma_load = 2
@@ -636,8 +671,7 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
                                maxrregcount=opts['maxrregcount'])
     emit_kwargs = dict(
         tile_cols=opts['tile_cols'],
-        warps_per_block=opts['warps_per_block'],
-        min_blocks_per_sm=opts['min_blocks_per_sm'],
+        warps_per_block=wpb, min_blocks_per_sm=mbs,
         tma_load=tma_load, tma_store=tma_store, derived=derived,
         debug_nostore=opts['debug_nostore'],
         tile_bufs=opts['tile_bufs'], debug_reps=opts['debug_reps'],
@@ -652,14 +686,15 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     if shards == 'auto':
         big = prog.stats()['varying_cost'] >= 40000 and len(parts) >= 4
         shards = min(len(parts), os.cpu_count() or 1, 16) if big else 1
+        # a module's TMA descriptors travel as one kernel parameter
+        shards = max(shards, -(-len(parts) // 96))
     shards = max(1, min(int(shards), len(parts)))
     if shards == 1:
         ranges = [None]
     else:
         # contiguous chunks of groups with balanced cost
-        costs = [prog.tape.cost(prog.group_nodes(range(r0, r1),
-                                                 set(derived) or None))
-                 for r0, r1 in parts]
+        costs = [prog.range_cost(c0, c1, set(derived) or None)
+                 for c0, c1 in parts]
         total = float(sum(costs)) or 1.0
         cuts, acc = [], 0.0
         for g, c in enumerate(costs[:-1]):

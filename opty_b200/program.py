@@ -182,6 +182,60 @@ class CollocationProgram(object):
         return [i for i in ids if T.varying[i] and T.op[i] != ir.VIN and
                 not (stop and i in stop)]
 
+    def range_roots(self, c0, c1):
+        """Outputs owned by the column range ``[c0, c1)`` of the flattened
+        ``M*P`` node block: its Jacobian entries and the residuals of the
+        rows whose first column lies in the range."""
+        P = self.P
+        roots = []
+        for col in range(c0, c1):
+            j, k = divmod(col, P)
+            if k == 0 and self.con:
+                roots.append(self.con[j])
+            roots.append(self.jac[j][k])
+        return roots
+
+    def range_nodes(self, c0, c1, stop=None):
+        """Like :meth:`group_nodes` for a column range."""
+        T = self.tape
+        roots = self.range_roots(c0, c1)
+        ids = self._reachable_stop(roots, stop) if stop else T.reachable(roots)
+        return [i for i in ids if T.varying[i] and T.op[i] != ir.VIN and
+                not (stop and i in stop)]
+
+    def range_cost(self, c0, c1, stop=None):
+        carved = getattr(self, 'carved', None)
+        stored = (c1 - c0) if not carved else \
+            (c1 - c0) - sum(carved[c0:c1])
+        return self.tape.cost(self.range_nodes(c0, c1, stop)) + 2.0 * stored
+
+    def split_heavy(self, cparts, max_cost, col_align=2, min_cols=16,
+                    stop=None):
+        """Splits column ranges whose body would cost more than ``max_cost``
+        into column blocks of about that cost.  Large bodies (one equation of
+        the 50-link chain is 20 k operations) exhaust the register file --
+        ptxas spills kilobytes per thread to local memory -- and the
+        instruction caches; the partials of one equation share little beyond
+        the inputs, so column blocks recompute little."""
+        out = []
+        for c0, c1 in cparts:
+            cost = self.range_cost(c0, c1, stop)
+            pieces = int(-(-cost // max_cost))
+            width = c1 - c0
+            if pieces <= 1 or width < 2 * min_cols:
+                out.append((c0, c1))
+                continue
+            step = -(-width // pieces)
+            step = max(min_cols, -(-step // col_align) * col_align)
+            c = c0
+            while c < c1:
+                e = min(c1, c + step)
+                if c1 - e < min_cols // 2:
+                    e = c1
+                out.append((c, e))
+                c = e
+        return out
+
     def _reachable_stop(self, roots, stop):
         T = self.tape
         seen = set()
@@ -203,8 +257,8 @@ class CollocationProgram(object):
         least two groups need.  Returns tape ids, most valuable first."""
         T = self.tape
         use = {}
-        for r0, r1 in parts:
-            for i in self.group_nodes(range(r0, r1)):
+        for c0, c1 in parts:
+            for i in self.range_nodes(c0, c1):
                 if ir.OP_COST[T.op[i]] >= min_cost:
                     use[i] = use.get(i, 0) + 1
         cand = [i for i, c in use.items() if c >= 2]

@@ -12,9 +12,9 @@ import numpy as np
 
 from . import build
 
-OPTY_MAX_GROUPS = 64
-OPTY_MAX_SEGMENTS = 128
-ABI_VERSION = 4
+OPTY_MAX_GROUPS = 1024
+OPTY_MAX_SEGMENTS = 1024
+ABI_VERSION = 5
 
 EXPORTS = (
     'opty_b200_abi_version', 'opty_colloc_create', 'opty_colloc_destroy',

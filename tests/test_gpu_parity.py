@@ -223,6 +223,10 @@ def test_config2_kernel_variants_agree_bitwise(config2):
          'out_ring': 2},
         # the problem compiled as three modules (parallel nvcc runs)
         {'compile_shards': 3, 'groups': 8, 'out_ring': 2},
+        # equations cut into column blocks (22 groups), 8-warp blocks with
+        # direct input loads
+        {'max_body_cost': 600.0, 'groups': 8, 'warps_per_block': 8,
+         'min_blocks_per_sm': 1, 'tma_load': 'direct', 'compile_shards': 2},
     ]
     ref_con = ref_jac = None
     for opts in variants:

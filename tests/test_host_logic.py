@@ -317,6 +317,35 @@ def test_emitted_code_matches_reference_golden(name, make, groups):
     assert_values_close(jac, gold['jac'][:nn * M * P], row_len=P)
 
 
+@pytest.mark.parametrize('name,make', HARNESS_WORKLOADS[2:],
+                         ids=[f[0] for f in HARNESS_WORKLOADS[2:]])
+def test_column_block_groups_match_reference_golden(name, make):
+    """Equations whose body is too large are cut into column blocks
+    (``max_body_cost``); with constant runs carved out on top the blocks,
+    store segments and residual ownership must still cover every entry."""
+    gold = load_golden(name)
+    for opts in ({'groups': 2, 'max_body_cost': 150.0},
+                 {'groups': 3, 'max_body_cost': 90.0, 'const_runs': True,
+                  'const_run_min': 4}):
+        w = make()      # the seeded free vector continues the workload's rng
+        col = ConstraintCollocator(*w.collocator_args(),
+                                   **w.collocator_kwargs(), cuda_options=opts)
+        free = w.free(col.num_free)
+        from host_harness import _prepare_without_nvcc
+        prog, source, meta = _prepare_without_nvcc(col)
+        P = prog.P
+        cols = [g['cols'] for g in meta['groups']]
+        assert cols[0][0] == 0 and cols[-1][1] == prog.K
+        assert all(a[1] == b[0] for a, b in zip(cols, cols[1:]))
+        # at least one equation really was cut inside a row
+        assert any(c0 % P or c1 % P for c0, c1 in cols)
+        con, jac = host_evaluate(col, free)
+        M = col.num_eom
+        nn = col.num_collocation_nodes - 1
+        assert_values_close(con, gold['con'][:M * nn])
+        assert_values_close(jac, gold['jac'][:nn * M * P], row_len=P)
+
+
 @pytest.mark.parametrize('case', cases.product_cases(),
                          ids=lambda c: c.name)
 def test_emitted_code_known_answers(case):

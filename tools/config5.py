@@ -94,14 +94,14 @@ def prepare_one(w, derive_s):
     print(json.dumps(out), flush=True)
 
 
-def make_handle(dump, N):
+def make_handle(dump, N, node_range=None, device=0):
     from opty_b200 import runtime
     from opty_b200.direct_collocation import fill_kernel_config
     cfg = runtime.ColloCfg()
     fill_kernel_config(cfg, dump['meta'], dump['opts'])
-    cfg.device = 0
+    cfg.device = device
     cfg.N = N
-    cfg.node_lo, cfg.node_hi = 0, N - 1
+    cfg.node_lo, cfg.node_hi = node_range or (0, N - 1)
     for key in ('n', 'q', 'k', 'r', 's', 'pk', 'M', 'P'):
         setattr(cfg, key, dump[key])
     cfg.method = 1
@@ -180,5 +180,92 @@ def run():
     print(json.dumps(out))
 
 
+def run_sharded():
+    """torchrun entry: the 50 000-node problem sharded by nodes over the
+    GPUs of the box (BASELINE configs[4]: 8 x B200 with an NCCL all-gather of
+    the per-shard residual and Jacobian blocks)."""
+    import torch
+    import torch.distributed as dist
+    from opty_b200.sharding import _CudaArray, gather_vectors, node_shard
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    with open(DUMP) as f:
+        dump = json.load(f)
+    n, q, M, P = dump['n'], dump['q'], dump['M'], dump['P']
+    rng = np.random.default_rng(0)
+    for _ in range(dump['rng_param_draws']):
+        rng.random()
+    free = rng.standard_normal(dump['num_free_full'])
+    lo, hi = node_shard(N_FULL, rank, world)
+    h = make_handle(dump, N_FULL, (lo, hi), local)
+    h.upload_free(free)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    h.time_device_evals(2)
+    barrier()
+    ms = max_over_ranks(min(h.time_device_evals(5) / 5 for _ in range(3)))
+    barrier()
+    # NCCL all-gather of the shards' blocks straight from the device buffers
+    h.eval_device(sync=True)
+    bufs = h.device_buffers()
+    dev = torch.device('cuda', local)
+    con = torch.as_tensor(_CudaArray(bufs['con'], h.con_len, h), device=dev)
+    jac = torch.as_tensor(_CudaArray(bufs['jac'], h.jac_len, h), device=dev)
+    full_con, full_jac = gather_vectors(con, jac, N_FULL, M, dist)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        full_con, full_jac = gather_vectors(con, jac, N_FULL, M, dist)
+    barrier()
+    gather_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / 3)
+    # every rank's slice of the gathered vector is its own block
+    K = M * P
+    ok = bool(torch.equal(full_jac[lo * K:hi * K], jac))
+    checksum = float(full_jac.sum().item())
+    if rank == 0:
+        nnf = N_FULL - 1
+        B = 8 * ((n + q) * N_FULL + M * nnf + nnf * K)
+        print(json.dumps({
+            'workload': '{}-link chain, {} midpoint nodes'.format(
+                LINKS, N_FULL),
+            'tag': TAG, 'n_gpus': world, 'scaling': 'strong',
+            'device_ms_per_eval': ms, 'algorithmic_GB': B / 1e9,
+            'achieved_GBps_aggregate': B / ms / 1e6,
+            'nccl_allgather_ms': gather_ms,
+            'allgather_GB_per_rank_out': full_jac.numel() * 8 / 1e9,
+            'allgather_busbw_GBps': (full_jac.numel() * 8 / 1e9) *
+            (world - 1) / world / (gather_ms * 1e-3),
+            'own_block_intact': ok, 'jac_checksum': checksum}), flush=True)
+    h.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def profile():
+    """A few device-resident evaluations at OPTY_PROFILE_NODES nodes (for
+    ncu captures)."""
+    with open(DUMP) as f:
+        dump = json.load(f)
+    N = int(os.environ.get('OPTY_PROFILE_NODES', 10000))
+    h = make_handle(dump, N)
+    free = np.random.default_rng(0).standard_normal(
+        (dump['n'] + dump['q']) * N)
+    h.upload_free(free)
+    print('ms per eval', h.time_device_evals(3) / 3)
+    h.close()
+
+
 if __name__ == '__main__':
-    {'prepare': prepare, 'run': run}[sys.argv[1]]()
+    {'prepare': prepare, 'run': run, 'run_sharded': run_sharded,
+     'profile': profile}[sys.argv[1]]()
