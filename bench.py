@@ -213,6 +213,11 @@ def run_own_arm(args, rank, world, local_rank):
         dist.init_process_group('nccl', device_id=torch.device(
             'cuda', local_rank))
 
+    numa_cpus = None
+    if world > 1:
+        # pinned host buffers on the GPU's own socket (one process per GPU)
+        from opty_b200.sharding import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local_rank)
     w = build_workload(world)
     nn = NODES_PER_RANK - 1
     node_range = (rank * nn, (rank + 1) * nn)
@@ -310,6 +315,9 @@ def run_own_arm(args, rank, world, local_rank):
                 'l2': 'rotating {} device output sets ({:.0f} MB) > 126 MB '
                       'L2'.format(OUT_RING, OUT_RING * 8e-6 * (
                           prog.M * nn + nn * prog.K)),
+                'host_affinity': ('GPU-local CPU set ({} cores) per rank'
+                                  .format(len(numa_cpus)) if numa_cpus else
+                                  'default'),
                 'e2e_d2h': 'literal-only Jacobian column ranges are written '
                            'to the pinned buffer once and not re-copied; '
                            'copied columns: {}'.format(ranges),

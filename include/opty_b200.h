@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define OPTY_B200_ABI_VERSION 5
+#define OPTY_B200_ABI_VERSION 6
 #define OPTY_MAX_GROUPS 1024
 #define OPTY_MAX_SEGMENTS 1024
 
@@ -81,6 +81,9 @@ typedef struct opty_colloc_cfg {
   int32_t con_tail;         /* extra host slots after the M*(N-1) residuals */
   int32_t jac_tail;         /* extra host slots after the (N-1)*M*P partials */
   int32_t prefetch_jac;     /* opty_colloc_constraints starts the Jacobian D2H speculatively */
+  int32_t persistent;       /* module holds the persistent main kernel: one block per SM bound to one
+                               group, launched along the schedule of opty_colloc_set_schedule, the
+                               pre-pass as phase 0 of the same (cooperative) launch */
   int32_t num_segments;     /* store segments: column runs of the node block written by the group bodies */
   int32_t primary_segments; /* segments [0, primary_segments) belong to the module given to
                                opty_colloc_create; the rest to modules added with opty_colloc_add_module */
@@ -161,6 +164,17 @@ int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t*
  * invariants and pre-pass kernels. */
 int opty_colloc_add_module(opty_colloc_t* h, const void* cubin, size_t cubin_bytes, int seg_first,
                            int seg_count, int num_groups);
+
+/* Persistent main kernel only: the block -> work table, one (group, first tile,
+ * end tile) triple per block (group = index inside the module, tiles of 32
+ * nodes); every (group, tile) pair must be covered exactly once and there may
+ * be at most one block per SM.  Replaces the `prange` node loop's static
+ * OpenMP schedule (opty/utils.py:716-741) with a measured one. */
+int opty_colloc_set_schedule(opty_colloc_t* h, int num_blocks, const int32_t* triples);
+
+/* clock64 ticks every block of the last persistent launch spent in its group
+ * phase (input for re-balancing the schedule). */
+int opty_colloc_block_clocks(opty_colloc_t* h, int num_blocks, int64_t* clocks);
 
 /* Registers the constant column runs of the node block (cfg.const_image_doubles
  * columns in total): run i covers columns [col0[i], col0[i]+len[i]) (even start

@@ -68,9 +68,14 @@ def build_runtime(force=False, verbose=False):
     return RUNTIME_LIB
 
 
-def _header_digest():
+def _header_digest(source=''):
     hasher = hashlib.sha256()
-    for name in ('colloc_kernel.cuh', 'colloc_params.h'):
+    names = ['colloc_kernel.cuh', 'colloc_params.h']
+    # optional skeleton pieces only count for the modules that include them
+    for extra in ('colloc_persistent.cuh',):
+        if '#include "{}"'.format(extra) in source:
+            names.append(extra)
+    for name in names:
         with open(os.path.join(CSRC, name), 'rb') as f:
             hasher.update(f.read())
     return hasher.hexdigest()
@@ -97,7 +102,7 @@ def compile_module(source, flags, cache_dir=None, show_compile_output=False,
     hasher = hashlib.sha256()
     hasher.update(source.encode())
     hasher.update(' '.join(flags).encode())
-    hasher.update(_header_digest().encode())
+    hasher.update(_header_digest(source).encode())
     key = hasher.hexdigest()[:32]
     os.makedirs(cache_dir, exist_ok=True)
     cubin_path = os.path.join(cache_dir, 'colloc_{}.cubin'.format(key))

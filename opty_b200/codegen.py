@@ -181,7 +181,8 @@ def choose_tile_cols(requested):
 def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 min_blocks_per_sm=4, tma_load=True, tma_store=True,
                 derived=(), debug_nostore=False, tile_bufs=2, debug_reps=1,
-                const_runs=(), only_groups=None, with_aux=True):
+                const_runs=(), only_groups=None, with_aux=True,
+                persistent=False, tile_major=False):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block;
     a group also owns the residuals of the rows that start inside it).  ``derived`` lists the tape ids
@@ -195,11 +196,16 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     ``only_groups = (g0, g1)`` the module contains the bodies and the main
     kernel of groups ``g0 .. g1-1`` only (group and store-segment indices
     inside it are local); ``with_aux=False`` leaves out the invariants and
-    pre-pass kernels (the first module carries them)."""
+    pre-pass kernels (the first module carries them).
+
+    ``persistent=True`` emits the persistent variant of the main kernel
+    (``csrc/colloc_persistent.cuh``): one block per SM bound to one group,
+    warps looping over node tiles along a host-made schedule, the pre-pass
+    as phase 0 of the same launch."""
     T = prog.tape
     M, P, K, R = prog.M, prog.P, prog.K, prog.R
     C = choose_tile_cols(tile_cols)
-    if warps_per_block > 4 and warps_per_block % 4:
+    if warps_per_block > 4 and warps_per_block % 4 and not persistent:
         raise ValueError('warps_per_block above 4 must be a multiple of 4')
     ninv = len(prog.inv_nodes)
     derived = list(derived)
@@ -255,16 +261,26 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     w('#define OPTY_NGROUPS {}'.format(g1 - g0))
     w('#define OPTY_NINV {}'.format(max(ninv, 1)))
     w('#define OPTY_NUNI {}'.format(max(prog.num_uniform, 1)))
-    w('#define OPTY_WARPS {}'.format(warps_per_block))
-    w('#define OPTY_MIN_BLOCKS {}'.format(min_blocks_per_sm))
+    if persistent:
+        # the base skeleton is used with its per-warp geometry
+        w('#define OPTY_WARPS 1')
+        w('#define OPTY_PWARPS {}'.format(warps_per_block))
+        w('#define OPTY_MIN_BLOCKS 1')
+    else:
+        w('#define OPTY_WARPS {}'.format(warps_per_block))
+        w('#define OPTY_MIN_BLOCKS {}'.format(min_blocks_per_sm))
     w('#define OPTY_TMA_LOAD {}'.format(int(tma_load)))
     w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
     w('#define OPTY_NBUF {}'.format(int(tile_bufs)))
+    if tile_major:
+        w('#define OPTY_TILE_MAJOR 1')
     if debug_nostore:
         w('#define OPTY_DEBUG_NOSTORE {}'.format(int(debug_nostore)))
     if debug_reps != 1:
         w('#define OPTY_DEBUG_REPS {}'.format(int(debug_reps)))
     w('#include "colloc_kernel.cuh"')
+    if persistent:
+        w('#include "colloc_persistent.cuh"')
     w('')
 
     # ---- invariants kernel -------------------------------------------
@@ -311,24 +327,44 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 const_inv.append(prog.inv_index[e])
     pre_ops = 0
     if with_aux:
-        w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
-        w('opty_colloc_pre(const OptyParams p)')
-        w('{')
-        w('  OPTY_PRE_BEGIN();')
-        w('  switch (opty_pg) {')
+        pre_cases = []
         for pg, ks in enumerate(pre_chunks):
             bw = _BodyWriter(prog, 'pre')
             for k in ks:
                 bw.need(derived[k])
                 bw.lines.append('OPTY_DRV({}, {});'.format(
                     k, bw.ref(derived[k])))
-            w('    case {}: {{'.format(pg))
-            for line in bw.lines:
-                w('      ' + line)
-            w('    } break;')
+            pre_cases.append('    case {}: {{'.format(pg))
+            pre_cases.extend('      ' + line for line in bw.lines)
+            pre_cases.append('    } break;')
             pre_ops += bw.num_ops
-        w('    default: break;')
-        w('  }')
+        if persistent:
+            # phase 0 of the persistent kernel calls the same bodies
+            w('static __device__ void opty_pre_unit(const OptyParams& p, '
+              'const int node, const int opty_pg)')
+            w('{')
+            w('  const double* xg = p.traj + node;')
+            w('  double* drv = p.traj + (long long)OPTY_R * p.ldt + node;')
+            w('  switch (opty_pg) {')
+            for line in pre_cases:
+                w(line)
+            w('    default: break;')
+            w('  }')
+            w('}')
+            w('')
+        w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
+        w('opty_colloc_pre(const OptyParams p)')
+        w('{')
+        w('  OPTY_PRE_BEGIN();')
+        if persistent:
+            w('  opty_pre_unit(p, node, opty_pg);')
+            w('  (void)xg; (void)drv;')
+        else:
+            w('  switch (opty_pg) {')
+            for line in pre_cases:
+                w(line)
+            w('    default: break;')
+            w('  }')
         w('}')
         w('')
 
@@ -414,25 +450,44 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     w('__device__ const int opty_group_order[OPTY_NGROUPS] = {{{}}};'.format(
         ', '.join(str(g) for g in order)))
     w('')
-    w('extern "C" __global__ void __launch_bounds__(OPTY_THREADS, '
-      'OPTY_MIN_BLOCKS)')
-    w('opty_colloc_eval(const __grid_constant__ OptyTmaps tm, '
-      'const OptyParams p)')
-    w('{')
-    w('  OPTY_KERNEL_BEGIN()')
-    if debug_reps != 1:
-        # measurement aid: the same tile is evaluated several times, passes
-        # after the first find the group body in the instruction caches
-        w('#pragma unroll 1')
-        w('  for (int opty_rep = 0; opty_rep < OPTY_DEBUG_REPS; ++opty_rep)')
-    w('  switch (opty_g) {')
-    for g in range(g0, g1):
-        w('    case {}: opty_group_{}(ctx); break;'.format(g - g0, g))
-    w('    default: break;')
-    w('  }')
-    w('  OPTY_KERNEL_END()')
-    w('}')
-    w('')
+    if persistent:
+        w('extern "C" __global__ void __launch_bounds__(OPTY_PTHREADS, 1)')
+        w('opty_colloc_eval(const __grid_constant__ OptyTmaps tm, '
+          'const OptyParams p, const OptyPersist ps)')
+        w('{')
+        w('  OPTY_PERSIST_BEGIN()')
+        w('  OPTY_PERSIST_LOOP_BEGIN()')
+        w('  switch (opty_g) {')
+        for g in range(g0, g1):
+            w('    case {}: opty_group_{}(ctx); break;'.format(g - g0, g))
+        w('    default: break;')
+        w('  }')
+        w('  OPTY_PERSIST_LOOP_END()')
+        w('  OPTY_PERSIST_END()')
+        w('}')
+        w('')
+    else:
+        w('extern "C" __global__ void __launch_bounds__(OPTY_THREADS, '
+          'OPTY_MIN_BLOCKS)')
+        w('opty_colloc_eval(const __grid_constant__ OptyTmaps tm, '
+          'const OptyParams p)')
+        w('{')
+        w('  OPTY_KERNEL_BEGIN()')
+        if debug_reps != 1:
+            # measurement aid: the same tile is evaluated several times,
+            # passes after the first find the group body in the instruction
+            # caches
+            w('#pragma unroll 1')
+            w('  for (int opty_rep = 0; opty_rep < OPTY_DEBUG_REPS; '
+              '++opty_rep)')
+        w('  switch (opty_g) {')
+        for g in range(g0, g1):
+            w('    case {}: opty_group_{}(ctx); break;'.format(g - g0, g))
+        w('    default: break;')
+        w('  }')
+        w('  OPTY_KERNEL_END()')
+        w('}')
+        w('')
 
     meta = {
         'emitter_version': EMITTER_VERSION,
@@ -457,6 +512,7 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         'tma_load': int(tma_load),
         'tma_store': bool(tma_store),
         'tile_bufs': int(tile_bufs),
+        'persistent': bool(persistent),
         'method': method,
         'entry_kind': prog.entry_kind(),
         'stats': prog.stats(),

@@ -249,6 +249,22 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
 //
 // The generated kernel body sits between OPTY_KERNEL_BEGIN and OPTY_KERNEL_END
 // and dispatches on `opty_g`.
+#ifndef OPTY_TILE_MAJOR
+#define OPTY_TILE_MAJOR 0
+#endif
+#if OPTY_TILE_MAJOR
+// tile-major dispatch: consecutive blocks are the groups of ONE node tile, so a
+// node row's 8 KB are written within a short time window (DRAM page locality of
+// the write-back stream) instead of in one phase per group
+#define OPTY_BLOCK_TO_WORK()                                                        \
+  const unsigned opty_lin = blockIdx.y * gridDim.x + blockIdx.x;                    \
+  const int opty_g = opty_group_order[opty_lin % OPTY_NGROUPS];                     \
+  const int tile_node0 = (int)(opty_lin / OPTY_NGROUPS) * OPTY_THREADS;
+#else
+#define OPTY_BLOCK_TO_WORK()                              \
+  const int opty_g = opty_group_order[blockIdx.y];        \
+  const int tile_node0 = blockIdx.x * OPTY_THREADS;
+#endif
 #define OPTY_KERNEL_BEGIN()                                                                              \
   extern __shared__ __align__(128) unsigned char opty_smem[];                                            \
   double* tiles = reinterpret_cast<double*>(opty_smem);                                                  \
@@ -260,8 +276,7 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
     if (threadIdx.x == 0) opty_mbar_init(bar, 1);                                                        \
     __syncthreads();                                                                                     \
   }                                                                                                      \
-  const int opty_g = opty_group_order[blockIdx.y];                                                       \
-  const int tile_node0 = blockIdx.x * OPTY_THREADS;                                                      \
+  OPTY_BLOCK_TO_WORK()                                                                                   \
   OPTY_STAGE_INPUT()                                                                                     \
   OptyCtx ctx;                                                                                           \
   ctx.lane = threadIdx.x & 31;                                                                           \

@@ -53,6 +53,8 @@ struct DriverApi {
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                            unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*LaunchCooperativeKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                      unsigned, CUstream, void**) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -84,6 +86,7 @@ int init_driver() {
   if ((rc = load_entry("cuModuleGetGlobal", &g_drv.ModuleGetGlobal))) return rc;
   if ((rc = load_entry("cuFuncSetAttribute", &g_drv.FuncSetAttribute))) return rc;
   if ((rc = load_entry("cuLaunchKernel", &g_drv.LaunchKernel))) return rc;
+  if ((rc = load_entry("cuLaunchCooperativeKernel", &g_drv.LaunchCooperativeKernel))) return rc;
   if ((rc = load_entry("cuGetErrorString", &g_drv.GetErrorString))) return rc;
   if ((rc = load_entry("cuTensorMapEncodeTiled", &g_drv.TensorMapEncodeTiled))) return rc;
   g_drv.ready = true;
@@ -238,8 +241,23 @@ opty_replicate_st_kernel(double* __restrict__ jac, long long K, const double* __
 
 }  // namespace
 
+// mirrors OptyPersist of csrc/colloc_persistent.cuh
+struct OptyPersistArgs {
+  const void* sched;
+  unsigned int* barrier;
+  unsigned int barrier_target;
+  long long* block_clocks;
+  int pre_units;
+};
+
 struct opty_colloc {
   opty_colloc_cfg cfg;
+  // persistent main kernel
+  int sched_blocks = 0;
+  void* d_sched = nullptr;          // int4 per block
+  unsigned int* d_barrier = nullptr;
+  long long* d_block_clocks = nullptr;
+  unsigned int barrier_epoch = 0;
   int nn = 0;          // constraint nodes of this handle
   int ncols = 0;       // trajectory columns held (nn + 1)
   int R = 0;           // trajectory rows n + q + k
@@ -349,7 +367,7 @@ int build_tmaps_into(opty_colloc* h, int slot, int seg_first, int seg_count, std
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(blob.data());
   int rc;
   if (c.tma_load == 1) {
-    const uint32_t threads = 32u * c.warps_per_block;
+    const uint32_t threads = c.persistent ? 32u : 32u * c.warps_per_block;  // persistent: per-warp slices
     const uint32_t xbox = (threads <= 128u ? threads : 128u) + 2u;
     if ((rc = encode_2d(&maps[0], h->d_traj, (uint64_t)h->ncols, (uint64_t)h->RD, (uint64_t)h->ldt * 8, xbox,
                         (uint32_t)h->RD)))
@@ -359,7 +377,7 @@ int build_tmaps_into(opty_colloc* h, int slot, int seg_first, int seg_count, std
     for (int g = 0; g < seg_count; ++g) {
       if ((rc = encode_2d(&maps[1 + g], h->d_jac[slot] + c.seg_col0[seg_first + g],
                           (uint64_t)c.seg_ncols[seg_first + g], (uint64_t)h->nn, (uint64_t)h->K * 8,
-                          (uint32_t)c.tile_cols, 32u)))
+                          (uint32_t)c.tile_cols, c.persistent ? 32u * c.warps_per_block : 32u)))
         return rc;
     }
   }
@@ -427,6 +445,21 @@ int launch_eval(opty_colloc* h) {
   p.ldc = h->nn;
   p.n_nodes = h->nn;
   p.n_cols = h->ncols;
+  if (c.persistent) {
+    // one cooperative launch: phase 0 = pre-pass, grid barrier, then every block walks its schedule entry
+    if (h->sched_blocks < 1) return fail(OPTY_ERR_STATE, "opty_colloc_set_schedule must be called before evaluating");
+    OptyPersistArgs ps;
+    ps.sched = h->d_sched;
+    ps.barrier = h->d_barrier;
+    h->barrier_epoch += (unsigned)h->sched_blocks;
+    ps.barrier_target = h->barrier_epoch;
+    ps.block_clocks = h->d_block_clocks;
+    ps.pre_units = c.num_derived > 0 ? c.pre_groups : 0;
+    void* pargs[3] = {h->tmaps[h->ring].data(), &p, &ps};
+    DRV_CHECK(g_drv.LaunchCooperativeKernel(h->f_eval, (unsigned)h->sched_blocks, 1, 1, 32u * c.warps_per_block, 1, 1,
+                                            h->smem_bytes, (CUstream)h->stream, pargs));
+    h->launches++;
+  } else {
   if (c.num_derived > 0) {
     void* pargs[1] = {&p};
     DRV_CHECK(g_drv.LaunchKernel(h->f_pre, (unsigned)((h->nn + 127) / 128), (unsigned)c.pre_groups, 1, 128, 1, 1, 0,
@@ -437,6 +470,7 @@ int launch_eval(opty_colloc* h) {
   DRV_CHECK(g_drv.LaunchKernel(h->f_eval, h->grid_x, (unsigned)c.num_groups, 1, 32u * c.warps_per_block, 1, 1, h->smem_bytes,
                                (CUstream)h->stream, args, nullptr));
   h->launches++;
+  }
   for (auto& em : h->extra) {
     void* eargs[2] = {em.tmaps[h->ring].data(), &p};
     DRV_CHECK(g_drv.LaunchKernel(em.f_eval, h->grid_x, (unsigned)em.num_groups, 1, 32u * c.warps_per_block, 1, 1,
@@ -552,7 +586,7 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   if (cfg->primary_segments > 240)
     return fail(OPTY_ERR_ARG, "a module's TMA descriptors are one kernel parameter: at most 240 store segments per module");
   if (cfg->warps_per_block < 1 || cfg->warps_per_block > 32 ||
-      (cfg->warps_per_block > 4 && cfg->warps_per_block % 4 != 0) || cfg->tile_cols < 2 || (cfg->tile_cols & 1) ||
+      (cfg->warps_per_block > 4 && cfg->warps_per_block % 4 != 0 && !cfg->persistent) || cfg->tile_cols < 2 || (cfg->tile_cols & 1) ||
       cfg->tile_cols > 256)
     return fail(OPTY_ERR_ARG, "invalid kernel geometry");
   if (cfg->out_ring < 1 || cfg->out_ring > 64) return fail(OPTY_ERR_ARG, "invalid out_ring");
@@ -672,6 +706,17 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   const unsigned xin_bytes =
       cfg->tma_load == 2 ? 0u : nseg * (unsigned)round_up((int64_t)h->RD * (xseg + 2u) * 8, 128);
   h->smem_bytes = tiles_bytes + xin_bytes + 128u;
+  if (cfg->persistent) {
+    if (cfg->warps_per_block > 8)
+      return (opty_colloc_destroy(h), fail(OPTY_ERR_ARG, "the persistent kernel supports at most 8 warps per block"));
+    if (cfg->tma_load != 1 || !cfg->tma_store || elementwise)
+      return (opty_colloc_destroy(h), fail(OPTY_ERR_ARG, "the persistent kernel needs TMA input staging and TMA stores"));
+    // per warp: its staging tiles and its own [R+D][34] input slice, one mbarrier each
+    const unsigned slice = (unsigned)round_up((int64_t)h->RD * 34 * 8, 128);
+    h->smem_bytes = tiles_bytes + (unsigned)cfg->warps_per_block * slice + 8u * cfg->warps_per_block + 128u;
+    CREATE_RT(cudaMalloc(&h->d_barrier, sizeof(unsigned int)));
+    CREATE_RT(cudaMemset(h->d_barrier, 0, sizeof(unsigned int)));
+  }
   if (const char* pad = getenv("OPTY_B200_DEBUG_SMEM_FLOOR")) {
     // measurement aid: a larger dynamic shared-memory request caps the resident blocks per SM
     const unsigned floor_bytes = (unsigned)atoi(pad);
@@ -696,6 +741,9 @@ int opty_colloc_destroy(opty_colloc_t* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->repl_stream) cudaStreamSynchronize(h->repl_stream);
+  cudaFree(h->d_sched);
+  cudaFree(h->d_barrier);
+  cudaFree(h->d_block_clocks);
   cudaFree(h->d_repl_lit);
   cudaFree(h->d_repl_inv);
   cudaFree(h->d_repl_off);
@@ -912,6 +960,53 @@ int opty_colloc_add_module(opty_colloc_t* h, const void* cubin, size_t cubin_byt
   h->extra.push_back(std::move(em));
   h->inv_dirty = true;
   h->evaluated = false;
+  return OPTY_OK;
+}
+
+int opty_colloc_set_schedule(opty_colloc_t* h, int num_blocks, const int32_t* triples) {
+  if (!h || !triples || num_blocks < 1) return fail(OPTY_ERR_ARG, "invalid argument");
+  const opty_colloc_cfg& c = h->cfg;
+  if (!c.persistent) return fail(OPTY_ERR_ARG, "the module was not emitted with the persistent kernel");
+  if (num_blocks > h->num_sms) return fail(OPTY_ERR_ARG, "at most one block per SM");
+  const int n_tiles = (h->nn + 31) / 32;
+  // every (group, tile) pair exactly once
+  std::vector<int> covered((size_t)c.num_groups * n_tiles, 0);
+  std::vector<int32_t> table((size_t)num_blocks * 4, 0);
+  for (int b = 0; b < num_blocks; ++b) {
+    const int g = triples[3 * b], t0 = triples[3 * b + 1], t1 = triples[3 * b + 2];
+    if (g < 0 || g >= c.num_groups || t0 < 0 || t1 < t0 || t1 > n_tiles)
+      return fail(OPTY_ERR_ARG, "schedule entry out of range");
+    for (int t = t0; t < t1; ++t) covered[(size_t)g * n_tiles + t]++;
+    table[4 * b] = g;
+    table[4 * b + 1] = t0;
+    table[4 * b + 2] = t1;
+  }
+  for (int v : covered)
+    if (v != 1) return fail(OPTY_ERR_ARG, "the schedule must cover every (group, tile) pair exactly once");
+  RT_CHECK(cudaSetDevice(c.device));
+  RT_CHECK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_sched);
+  cudaFree(h->d_block_clocks);
+  h->d_sched = nullptr;
+  h->d_block_clocks = nullptr;
+  RT_CHECK(cudaMalloc(&h->d_sched, (size_t)num_blocks * 16));
+  RT_CHECK(cudaMalloc(&h->d_block_clocks, (size_t)num_blocks * 8));
+  RT_CHECK(cudaMemcpy(h->d_sched, table.data(), (size_t)num_blocks * 16, cudaMemcpyHostToDevice));
+  RT_CHECK(cudaMemset(h->d_block_clocks, 0, (size_t)num_blocks * 8));
+  // the barrier counter restarts with the new grid size
+  RT_CHECK(cudaMemset(h->d_barrier, 0, sizeof(unsigned int)));
+  h->barrier_epoch = 0;
+  h->sched_blocks = num_blocks;
+  h->evaluated = false;
+  return OPTY_OK;
+}
+
+int opty_colloc_block_clocks(opty_colloc_t* h, int num_blocks, int64_t* clocks) {
+  if (!h || !clocks || num_blocks != h->sched_blocks || !h->d_block_clocks)
+    return fail(OPTY_ERR_ARG, "invalid argument");
+  RT_CHECK(cudaSetDevice(h->cfg.device));
+  RT_CHECK(cudaStreamSynchronize(h->stream));
+  RT_CHECK(cudaMemcpy(clocks, h->d_block_clocks, (size_t)num_blocks * 8, cudaMemcpyDeviceToHost));
   return OPTY_OK;
 }
 

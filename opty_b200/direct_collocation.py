@@ -82,6 +82,12 @@ DEFAULT_CUDA_OPTIONS = {
                                 # equation (residual + d/dq_j) carries 80 % of
                                 # its operations, so the largest body hardly
                                 # shrinks while the total work doubles
+    'tile_major': False,        # dispatch order of the grid kernel: the groups
+                                # of one node tile next to each other
+    'persistent': False,        # persistent main kernel: one block per SM
+                                # bound to one group, measured static schedule,
+                                # pre-pass as phase 0 of the same launch
+    'persistent_tune': 2,       # re-balancing passes of that schedule
     'compile_shards': 'auto',   # modules compiled in parallel (large problems)
     'target_warps': 148 * 16,
     'max_group_cost': 6000.0,
@@ -675,7 +681,14 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         tma_load=tma_load, tma_store=tma_store, derived=derived,
         debug_nostore=opts['debug_nostore'],
         tile_bufs=opts['tile_bufs'], debug_reps=opts['debug_reps'],
-        const_runs=const_runs)
+        const_runs=const_runs, persistent=bool(opts['persistent']),
+        tile_major=bool(opts['tile_major']))
+    if opts['persistent']:
+        if tma_load != 1 or not tma_store or const_runs:
+            raise ValueError('The persistent kernel needs TMA input staging '
+                             'and TMA stores and does not combine with '
+                             'const_runs.')
+        opts = dict(opts, compile_shards=1)
 
     # Large problems are split into several modules (contiguous ranges of
     # output groups) that nvcc compiles in parallel; the runtime launches one
@@ -745,6 +758,41 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     return parts, derived, source, meta, cubin, cubin_path, cache_hit
 
 
+def make_schedule(round_costs, n_tiles, num_blocks, warps):
+    """Static schedule of the persistent kernel: ``round_costs[g]`` is the
+    (measured or estimated) time one block needs for one round of ``warps``
+    tiles of group ``g``.  Every group gets a number of blocks -- one block
+    per SM -- such that the slowest block is as fast as possible (greedy on
+    the step function ``ceil(tiles / warps) * round_cost``), and its tiles
+    are dealt out evenly.  Returns ``[(group, first_tile, end_tile), ...]``."""
+    G = len(round_costs)
+    if G > num_blocks:
+        raise ValueError('The persistent kernel needs at most one output '
+                         'group per SM ({} groups, {} SMs).'.format(
+                             G, num_blocks))
+    blocks = [1] * G
+
+    def block_time(g):
+        tiles = -(-n_tiles // blocks[g])
+        return -(-tiles // warps) * round_costs[g]
+
+    for _ in range(num_blocks - G):
+        g = max(range(G), key=block_time)
+        if blocks[g] >= n_tiles:
+            break
+        blocks[g] += 1
+    triples = []
+    for g in range(G):
+        base, extra = divmod(n_tiles, blocks[g])
+        t0 = 0
+        for b in range(blocks[g]):
+            k = base + (1 if b < extra else 0)
+            if k:
+                triples.append((g, t0, t0 + k))
+            t0 += k
+    return triples
+
+
 def attach_extra_modules(handle, meta):
     """Loads the additional modules of a problem that was compiled in
     several pieces into ``handle``."""
@@ -769,6 +817,7 @@ def fill_kernel_config(cfg, meta, opts):
     cfg.tma_store = int(meta['tma_store'])
     cfg.out_ring = int(opts['out_ring'])
     cfg.prefetch_jac = int(bool(opts.get('prefetch_jacobian', False)))
+    cfg.persistent = int(bool(meta.get('persistent', False)))
     cfg.num_segments = len(meta['segments'])
     seg_range = meta.get('segment_range', [0, len(meta['segments'])])
     cfg.primary_segments = seg_range[1] - seg_range[0]
@@ -849,6 +898,9 @@ class _CudaEvaluator(object):
         self.con_len = M * nn
         self.jac_len = nn * K
 
+        if meta.get('persistent'):
+            self._setup_persistent_schedule(opts)
+
         self._callable_known = any(
             _is_callable_value(v) for v in col.known_trajectory_map.values())
         self._push_known(None)
@@ -875,6 +927,48 @@ class _CudaEvaluator(object):
             params = np.array([float(col.known_parameter_map[p])
                                for p in col.known_parameters])
         self.handle.set_known(traj, params)
+
+    def _setup_persistent_schedule(self, opts):
+        """Initial schedule from the emitter's cost model; it is re-balanced
+        from measured block times on the first evaluations
+        (:meth:`tune_schedule`)."""
+        import torch
+        meta = self.meta
+        self._sched_sms = torch.cuda.get_device_properties(
+            self.col._device).multi_processor_count
+        self._sched_warps = meta['warps_per_block']
+        self._sched_tiles = -(-self.nn // 32)
+        self._round_costs = [20.0 * g['ops'] + 43.0 * g['ncols']
+                             for g in meta['groups']]
+        self._sched = make_schedule(self._round_costs, self._sched_tiles,
+                                    self._sched_sms, self._sched_warps)
+        self.handle.set_schedule(self._sched)
+        self._tune_left = int(opts['persistent_tune'])
+
+    def tune_schedule(self, evals=3):
+        """One re-balancing pass: times ``evals`` evaluations of the resident
+        free vector, converts every block's clock count into a per-round cost
+        of its group and rebuilds the schedule."""
+        h = self.handle
+        W = self._sched_warps
+        acc = np.zeros(len(self._round_costs))
+        cnt = np.zeros(len(self._round_costs))
+        for _ in range(evals):
+            h.eval_device(sync=True)
+            clocks = h.block_clocks()
+            for (g, t0, t1), c in zip(self._sched, clocks):
+                rounds = -(-(t1 - t0) // W)
+                acc[g] += c / rounds
+                cnt[g] += 1
+        self._round_costs = list(acc / np.maximum(cnt, 1))
+        self._sched = make_schedule(self._round_costs, self._sched_tiles,
+                                    self._sched_sms, W)
+        h.set_schedule(self._sched)
+
+    def _maybe_tune(self):
+        while getattr(self, '_tune_left', 0) > 0:
+            self._tune_left -= 1
+            self.tune_schedule()
 
     def _setup_constant_elision(self):
         """Jacobian columns whose value cannot change between calls --
@@ -922,6 +1016,9 @@ class _CudaEvaluator(object):
         free = self._check_free(free)
         if self._callable_known:
             self._push_known(free)
+        if getattr(self, '_tune_left', 0) > 0:
+            self.handle.upload_free(free)
+            self._maybe_tune()
         buf = self.handle.constraints(free)
         if self.num_inst:
             buf[self.con_len:] = self.col.eval_instance_constraints(free)
@@ -931,6 +1028,9 @@ class _CudaEvaluator(object):
         free = self._check_free(free)
         if self._callable_known:
             self._push_known(free)
+        if getattr(self, '_tune_left', 0) > 0:
+            self.handle.upload_free(free)
+            self._maybe_tune()
         buf = self.handle.jacobian(free)
         if self.num_inst:
             buf[self.jac_len:] = \

@@ -14,7 +14,7 @@ from . import build
 
 OPTY_MAX_GROUPS = 1024
 OPTY_MAX_SEGMENTS = 1024
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 EXPORTS = (
     'opty_b200_abi_version', 'opty_colloc_create', 'opty_colloc_destroy',
@@ -23,6 +23,7 @@ EXPORTS = (
     'opty_colloc_jacobian', 'opty_colloc_host_buffers',
     'opty_colloc_device_buffers', 'opty_colloc_set_d2h_columns',
     'opty_colloc_set_const_runs', 'opty_colloc_add_module',
+    'opty_colloc_set_schedule', 'opty_colloc_block_clocks',
     'opty_colloc_last_kernel_ms', 'opty_colloc_time_device_evals',
     'opty_colloc_launch_count',
     'opty_colloc_jacobian_indices', 'opty_colloc_last_error',
@@ -58,6 +59,7 @@ class ColloCfg(ctypes.Structure):
         ('con_tail', ctypes.c_int32),
         ('jac_tail', ctypes.c_int32),
         ('prefetch_jac', ctypes.c_int32),
+        ('persistent', ctypes.c_int32),
         ('num_segments', ctypes.c_int32),
         ('primary_segments', ctypes.c_int32),
         ('const_image_doubles', ctypes.c_int32),
@@ -106,6 +108,8 @@ def load_library(path=None):
     lib.opty_colloc_add_module.argtypes = [c_vp, c_vp, ctypes.c_size_t,
                                            ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int]
+    lib.opty_colloc_set_schedule.argtypes = [c_vp, ctypes.c_int, c_vp]
+    lib.opty_colloc_block_clocks.argtypes = [c_vp, ctypes.c_int, c_vp]
     lib.opty_colloc_set_const_runs.argtypes = [c_vp, ctypes.c_int, c_vp, c_vp,
                                                c_vp, c_vp]
     lib.opty_colloc_last_kernel_ms.argtypes = [c_vp,
@@ -274,6 +278,20 @@ class ColloHandle(object):
         _check(self.lib, self.lib.opty_colloc_add_module(
             self._h, ctypes.cast(buf, ctypes.c_void_p), len(cubin),
             int(seg_first), int(seg_count), int(num_groups)))
+
+    def set_schedule(self, triples):
+        """``triples``: one ``(group, first_tile, end_tile)`` per block of the
+        persistent kernel."""
+        arr = np.ascontiguousarray(triples, dtype=np.int32).reshape(-1, 3)
+        _check(self.lib, self.lib.opty_colloc_set_schedule(
+            self._h, arr.shape[0], arr.ctypes.data))
+        self._sched_blocks = arr.shape[0]
+
+    def block_clocks(self):
+        out = np.zeros(self._sched_blocks, dtype=np.int64)
+        _check(self.lib, self.lib.opty_colloc_block_clocks(
+            self._h, self._sched_blocks, out.ctypes.data))
+        return out
 
     def set_const_runs(self, runs, lit, inv_idx):
         """``runs``: list of ``(col0, length)``; ``lit`` / ``inv_idx``: the

@@ -32,6 +32,32 @@ def node_shard(num_collocation_nodes, rank, world_size):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def bind_to_gpu_numa_node(device):
+    """Pins the calling process to the CPU cores that are local to GPU
+    ``device`` (NVML's CPU affinity of the device) before the pinned host
+    buffers are allocated, so that the Jacobian lands in host memory on the
+    GPU's own socket.  With one process per GPU the device->host copies of the
+    ranks then do not all cross the inter-socket link.  Returns the CPU set or
+    ``None`` when NVML is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words)
+                for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:       # no NVML / not permitted: keep the default
+        return None
+    return None
+
+
 def all_shards(num_collocation_nodes, world_size):
     return [node_shard(num_collocation_nodes, r, world_size)
             for r in range(world_size)]
@@ -124,6 +150,8 @@ class ShardedCollocator(object):
         self.rank, self.world_size = rank, world_size
         N = args[2] if len(args) > 2 else kwargs['num_collocation_nodes']
         self.shards = all_shards(N, world_size)
+        if world_size > 1 and device is not None:
+            bind_to_gpu_numa_node(device)
         self.collocator = ConstraintCollocator(
             *args, node_range=self.shards[rank], device=device, **kwargs)
         self._con = self.collocator.generate_constraint_function()

@@ -227,6 +227,12 @@ def test_config2_kernel_variants_agree_bitwise(config2):
         # direct input loads
         {'max_body_cost': 600.0, 'groups': 8, 'warps_per_block': 8,
          'min_blocks_per_sm': 1, 'tma_load': 'direct', 'compile_shards': 2},
+        # persistent kernel: one block per SM bound to a group, measured
+        # static schedule, pre-pass as phase 0, block-wide TMA stores
+        {'persistent': True, 'groups': 11, 'warps_per_block': 8,
+         'min_blocks_per_sm': 1},
+        # tile-major dispatch order of the grid kernel
+        {'tile_major': True, 'groups': 8},
     ]
     ref_con = ref_jac = None
     for opts in variants:

@@ -395,6 +395,28 @@ def test_compile_failure_raises_import_error():
         assert 'STDERR' in str(err.value)
 
 
+def test_persistent_schedule_covers_every_tile_once():
+    from opty_b200.direct_collocation import make_schedule
+    for costs, tiles, sms, warps in (([5.0, 1.0, 3.0], 313, 148, 8),
+                                     ([1.0] * 11, 40, 16, 4),
+                                     ([2.0, 9.0], 3, 148, 8)):
+        sched = make_schedule(costs, tiles, sms, warps)
+        assert len(sched) <= sms
+        seen = {}
+        for g, t0, t1 in sched:
+            assert 0 <= t0 < t1 <= tiles
+            for t in range(t0, t1):
+                assert (g, t) not in seen
+                seen[(g, t)] = 1
+        assert len(seen) == len(costs) * tiles
+    # expensive groups get more blocks than cheap ones
+    sched = make_schedule([5.0, 1.0, 3.0], 313, 148, 8)
+    blocks = [sum(1 for s in sched if s[0] == g) for g in range(3)]
+    assert blocks[0] > blocks[2] > blocks[1]
+    with pytest.raises(ValueError):
+        make_schedule([1.0] * 200, 10, 148, 8)
+
+
 def test_c_abi_library_exports_every_declared_symbol():
     lib = runtime.load_library()
     header = open(os.path.join(ROOT, 'include', 'opty_b200.h')).read()
