@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(256) store_kernel(const __grid_constant__ CUte
 struct Variant {
   const char* name;
   int mode, K, Kp, C, warps, nbuf, work, G;
+  int smem_floor = 0;  // > 0: request at least this much dynamic shared memory (caps the resident blocks per SM)
 };
 
 int main() {
@@ -132,23 +133,25 @@ int main() {
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
 
+  // session 2: does the TMA store stream overlap with arithmetic at the real kernel's occupancy
+  // (4 blocks x 2 warps per SM = 56 KB of shared memory per block)?
+  const int F = 56 * 1024;
   std::vector<Variant> vs = {
-      {"tma   store only          C30 G8", 0, 1012, 1012, 30, 2, 2, 0, 8},
-      {"lsu16 store only          C30 G8", 7, 1012, 1012, 30, 2, 1, 0, 8},
-      {"lsu16 store only          C62 G8", 7, 1012, 1012, 62, 2, 1, 0, 8},
-      {"lsu16 store only          C64 G8", 7, 1012, 1012, 64, 2, 1, 0, 8},
-      {"lsu16 store only          C128 G8", 7, 1012, 1012, 128, 2, 1, 0, 8},
-      {"lsu16 store only          C46 G11", 7, 1012, 1012, 46, 2, 1, 0, 11},
-      {"lsu16 store only  W4      C62 G8", 7, 1012, 1012, 62, 4, 1, 0, 8},
-      {"compute only w1000        C30 G8", 6, 1012, 1012, 30, 2, 2, 1000, 8},
-      {"tma   store+compute w1000 C30 G8", 0, 1012, 1012, 30, 2, 2, 1000, 8},
-      {"lsu16 store+compute w1000 C30 G8", 7, 1012, 1012, 30, 2, 1, 1000, 8},
-      {"lsu16 store+compute w1000 C62 G8", 7, 1012, 1012, 62, 2, 1, 2000, 8},
-      {"lsu16 store+compute w500  C30 G8", 7, 1012, 1012, 30, 2, 1, 500, 8},
-      {"tma   store+compute w500  C30 G8", 0, 1012, 1012, 30, 2, 2, 500, 8},
+      {"tma store only              C30 occ8", 0, 1012, 1012, 30, 2, 2, 0, 8, F},
+      {"tma store only              C30 occ-free", 0, 1012, 1012, 30, 2, 2, 0, 8, 0},
+      {"compute only w250           C30 occ8", 6, 1012, 1012, 30, 2, 2, 250, 8, F},
+      {"tma store+compute w250      C30 occ8", 0, 1012, 1012, 30, 2, 2, 250, 8, F},
+      {"compute only w500           C30 occ8", 6, 1012, 1012, 30, 2, 2, 500, 8, F},
+      {"tma store+compute w500      C30 occ8", 0, 1012, 1012, 30, 2, 2, 500, 8, F},
+      {"compute only w1000          C30 occ8", 6, 1012, 1012, 30, 2, 2, 1000, 8, F},
+      {"tma store+compute w1000     C30 occ8", 0, 1012, 1012, 30, 2, 2, 1000, 8, F},
+      {"tma store only              C62 occ8", 0, 1012, 1012, 62, 2, 2, 0, 8, F},
+      {"compute only w1000          C62 occ8", 6, 1012, 1012, 62, 2, 2, 1000, 8, F},
+      {"tma store+compute w1000     C62 occ8", 0, 1012, 1012, 62, 2, 2, 1000, 8, F},
+      {"tma store+compute w1000 B4  C30 occ8", 0, 1012, 1012, 30, 2, 4, 1000, 8, F},
+      {"tma store only  W1          C30 occ8", 0, 1012, 1012, 30, 1, 2, 0, 8, 28 * 1024},
+      {"tma store+compute w500 W1   C30 occ8", 0, 1012, 1012, 30, 1, 2, 500, 8, 28 * 1024},
   };
-
-
 
   for (const Variant& v : vs) {
     std::vector<CUtensorMap> maps(nring);
@@ -171,7 +174,8 @@ int main() {
     if (!ok) continue;
     const int threads = v.warps * 32;
     const int blocks = (nodes + threads - 1) / threads;
-    const size_t smem = (size_t)v.warps * v.nbuf * 32 * (v.C + 2) * 8 + 1024;
+    size_t smem = (size_t)v.warps * v.nbuf * 32 * (v.C + 2) * 8 + 1024;
+    if ((size_t)v.smem_floor > smem) smem = (size_t)v.smem_floor;
     auto launch = [&](int r) {
       switch (v.mode) {
         case 0:
