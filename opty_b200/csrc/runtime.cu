@@ -280,6 +280,9 @@ struct opty_colloc {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_copy = nullptr, ev_con = nullptr;
   bool jac_inflight = false;
+  std::vector<char> slot_copying;       // ring slots a speculative copy may still be reading
+  uint64_t eval_seq = 0;                // evaluations launched so far
+  uint64_t copy_seq = 0;                // evaluation the most recent speculative copy belongs to
 
   double* d_traj = nullptr;
   double* d_uni = nullptr;
@@ -388,11 +391,18 @@ int launch_eval(opty_colloc* h) {
   const opty_colloc_cfg& c = h->cfg;
   if (!h->known_set) return fail(OPTY_ERR_STATE, "opty_colloc_set_known must be called before evaluating");
   if (!h->free_valid) return fail(OPTY_ERR_STATE, "no free vector resident on the device");
-  if (h->jac_inflight) {
-    // a speculative Jacobian copy of the previous evaluation is still running:
-    // order the new kernels (and later copies into the pinned buffer) after it
-    RT_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
-    h->jac_inflight = false;
+  {
+    // Speculative Jacobian copies of earlier evaluations may still be reading their ring slot (IPOPT's
+    // line search asks for g at trial points without ever asking for jac_g there).  The new kernels only
+    // have to wait when they are about to overwrite a slot such a copy reads -- with out_ring >= 2 a
+    // rejected trial point does not stall the next evaluation behind 40-80 MB of PCIe traffic.
+    const int next_slot = (h->ring + 1) % c.out_ring;
+    if (h->slot_copying.size() != (size_t)c.out_ring) h->slot_copying.assign(c.out_ring, 0);
+    if (h->slot_copying[next_slot]) {
+      RT_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));  // ev_copy follows every copy queued so far
+      h->slot_copying.assign(c.out_ring, 0);
+      h->jac_inflight = false;
+    }
   }
   RT_CHECK(cudaEventRecord(h->ev0, h->stream));
   if (h->inv_dirty && c.num_inv > 0) {
@@ -413,6 +423,7 @@ int launch_eval(opty_colloc* h) {
   }
   h->inv_dirty = false;
   h->ring = (h->ring + 1) % c.out_ring;
+  h->eval_seq++;
   if (c.const_image_doubles > 0) {
     if (h->repl_chunks == 0)
       return fail(OPTY_ERR_STATE, "opty_colloc_set_const_runs must be called before evaluating");
@@ -839,6 +850,9 @@ int opty_colloc_constraints(opty_colloc_t* h, const double* free_host, double* c
     if ((rc = enqueue_jac_copy(h, h->copy_stream))) return rc;
     RT_CHECK(cudaEventRecord(h->ev_copy, h->copy_stream));
     h->jac_inflight = true;
+    h->copy_seq = h->eval_seq;
+    if (h->slot_copying.size() != (size_t)h->cfg.out_ring) h->slot_copying.assign(h->cfg.out_ring, 0);
+    h->slot_copying[h->ring] = 1;
   }
   if (!h->con_fetched) {
     RT_CHECK(cudaStreamSynchronize(h->stream));
@@ -856,10 +870,19 @@ int opty_colloc_jacobian(opty_colloc_t* h, const double* free_host, double* jac_
   if (!h->evaluated && (rc = launch_eval(h))) return rc;
   const size_t bytes = (size_t)h->nn * h->K * 8;
   if (!h->jac_fetched) {
-    if (h->jac_inflight) {
+    if (h->jac_inflight && h->copy_seq == h->eval_seq) {
+      // the speculative copy started by constraints() at this very point
       RT_CHECK(cudaEventSynchronize(h->ev_copy));
       h->jac_inflight = false;
+      h->slot_copying.assign(h->slot_copying.size(), 0);
     } else {
+      if (h->jac_inflight) {
+        // copies of other points are still in flight (rejected trial points): they target the same
+        // pinned buffer, so this one is ordered behind them
+        RT_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+        h->jac_inflight = false;
+        h->slot_copying.assign(h->slot_copying.size(), 0);
+      }
       if ((rc = enqueue_jac_copy(h, h->stream))) return rc;
       RT_CHECK(cudaStreamSynchronize(h->stream));
     }

@@ -294,9 +294,17 @@ def test_node_range_shards_reproduce_the_whole(config2):
 # ---------------------------------------------------------------------------
 # stand-in for BASELINE config 4 at a larger size, against the oracle
 # ---------------------------------------------------------------------------
-def test_config4_standin_against_oracle():
+@pytest.mark.parametrize('opts', [
+    {},
+    # persistent kernel on a backward-Euler problem with a known trajectory,
+    # free parameters and a free time interval (invariants change per call)
+    {'persistent': True, 'groups': 4, 'warps_per_block': 4,
+     'min_blocks_per_sm': 1},
+    {'const_runs': True, 'const_run_min': 4},
+], ids=['default', 'persistent', 'const_runs'])
+def test_config4_standin_against_oracle(opts):
     w = workloads.n_link_pendulum_torques(4, 2000)
-    col = _collocator(w)
+    col = _collocator(w, cuda_options=opts)
     free = w.free(col.num_free)
     orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
     con = col.generate_constraint_function()(free)
@@ -366,6 +374,32 @@ def test_problem_callback_surface():
     with pytest.raises(ValueError):
         prob.jacobian(np.zeros((153, 1)))
     prob.collocator.close()
+
+
+def test_line_search_call_pattern_with_output_ring():
+    """IPOPT's line search evaluates g at trial points without asking for
+    jac_g there; with ``out_ring=2`` those evaluations do not wait for the
+    speculative Jacobian copy of the previous point.  Whatever the call
+    order, every result must belong to the point it was asked at."""
+    w = workloads.n_link_pendulum(10, 40, seed=7)
+    col = _collocator(w, cuda_options={'out_ring': 2})
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    base = w.free(col.num_free)
+    pts = [base * (1.0 + 0.01 * i) for i in range(6)]
+    con_f = col.generate_constraint_function()
+    jac_f = col.generate_jacobian_function()
+    P = col._evaluator.program.P
+    # c = constraints, j = jacobian, digit = point
+    pattern = ['c0', 'j0', 'c1', 'c2', 'c3', 'j3', 'j4', 'c4', 'c5', 'c0',
+               'j0', 'j0', 'c1', 'j2', 'c2', 'c3', 'c4', 'c5', 'j5']
+    for step in pattern:
+        x = pts[int(step[1])]
+        if step[0] == 'c':
+            assert_values_close(con_f(x), orc.constraints(x))
+        else:
+            assert_values_close(np.array(jac_f(x)), orc.jacobian(x),
+                                row_len=P)
+    col.close()
 
 
 def test_callable_known_trajectory_sees_free():
