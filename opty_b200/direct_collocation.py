@@ -72,7 +72,9 @@ DEFAULT_CUDA_OPTIONS = {
     'const_run_min': 16,        # shortest run (columns) worth carving out
     'debug_nostore': False,     # measurement aid: skip Jacobian tile stores
     'debug_reps': 1,            # measurement aid: evaluate every tile n times
-    'out_ring': 1,              # device output sets to rotate through
+    'out_ring': 2,              # device output sets to rotate through (2: an
+                                # evaluation at a new point does not wait for
+                                # the speculative Jacobian copy of the last one)
     'use_sympy_cse': True,
     'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
     'prefetch_jacobian': True,  # constraints() starts the Jacobian D2H early
@@ -1163,6 +1165,18 @@ class Problem(_IpoptBase):
         self.upper_bound = ub
 
     # -- callbacks ----------------------------------------------------------
+    @property
+    def bounds(self):
+        """Variable bounds given at construction
+        (opty/direct_collocation.py:251-255)."""
+        return self._bounds
+
+    @property
+    def eom_bounds(self):
+        """Equation-of-motion bounds given at construction
+        (opty/direct_collocation.py:257-261)."""
+        return self._eom_bounds
+
     def objective(self, free):
         return self.obj(free) if self._obj_num_args == 1 else \
             self.obj(self, free)
@@ -1232,6 +1246,59 @@ class Problem(_IpoptBase):
             else:
                 raise ValueError('{} is not a free variable.'.format(var))
         return np.concatenate(out)
+
+    def _free_slices(self, variables):
+        """Index ranges of ``variables`` in the free vector, layout of
+        opty/direct_collocation.py:972-1002."""
+        col = self.collocator
+        N = col.num_collocation_nodes
+        n, q = col.num_states, col.num_unknown_input_trajectories
+        r = col.num_unknown_parameters
+        out = []
+        for var in variables:
+            if var in col.state_symbols:
+                i = col.state_symbols.index(var)
+                out.append((i * N, (i + 1) * N))
+            elif var in col.unknown_input_trajectories:
+                i = n + col.unknown_input_trajectories.index(var)
+                out.append((i * N, (i + 1) * N))
+            elif var in col.unknown_parameters:
+                i = (n + q) * N + col.unknown_parameters.index(var)
+                out.append((i, i + 1))
+            elif col._variable_duration and var == col.time_interval_symbol:
+                out.append(((n + q) * N + r, (n + q) * N + r + 1))
+            else:
+                raise ValueError('{} not an unknown in this problem.'.format(
+                    var))
+        return out
+
+    def fill_free(self, free, values, *variables):
+        """Replaces the entries of ``free`` that belong to ``variables`` by
+        ``values`` (stacked in the order of the variables), in place
+        (opty/direct_collocation.py:1004-1028)."""
+        idx = np.concatenate([np.arange(a, b)
+                              for a, b in self._free_slices(variables)])
+        free[idx] = values
+
+    def time_vector(self, solution=None, start_time=0.0):
+        """Time instances of the collocation nodes
+        (opty/direct_collocation.py:1097-1132)."""
+        col = self.collocator
+        N = col.num_collocation_nodes
+        if col._variable_duration:
+            if solution is None:
+                raise ValueError('Solution vector must be provided for '
+                                 'variable duration.')
+            h = solution[-1]
+            if h <= 0.0:
+                raise ValueError('Time interval must be strictly greater '
+                                 'than zero.')
+            if start_time >= h * (N - 1):
+                raise ValueError('Start time must be less than the final '
+                                 'time.')
+        else:
+            h = col.node_time_interval
+        return np.linspace(start_time, start_time + h * (N - 1), num=N)
 
     def parse_free(self, free):
         col = self.collocator

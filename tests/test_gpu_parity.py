@@ -376,6 +376,38 @@ def test_problem_callback_surface():
     prob.collocator.close()
 
 
+def test_problem_helpers_fill_free_and_time_vector():
+    """Host-side conveniences of the facade (opty/direct_collocation.py:
+    1004-1028, 1097-1132) (the facade creates its device handle at construction)."""
+    from opty_b200 import Problem
+    import sympy as sm
+    w = workloads.n_link_pendulum_torques(4, 50)
+    prob = Problem(lambda f: 0.0, lambda f: np.zeros_like(f),
+                   *w.collocator_args(), **w.collocator_kwargs(),
+                   bounds={w.states[0]: (-1.0, 1.0)})
+    col = prob.collocator
+    N = col.num_collocation_nodes
+    free = np.zeros(col.num_free)
+    x1 = w.states[1]
+    prob.fill_free(free, np.arange(N, dtype=float), x1)
+    assert np.array_equal(prob.extract_values(free, x1), np.arange(N))
+    assert np.count_nonzero(free) == N - 1
+    h = col.time_interval_symbol
+    prob.fill_free(free, 0.25, h)
+    assert free[-1] == 0.25
+    p0 = col.unknown_parameters[0]
+    prob.fill_free(free, np.hstack((np.ones(N), 3.0)), w.states[0], p0)
+    assert prob.extract_values(free, p0)[0] == 3.0
+    with pytest.raises(ValueError):
+        prob.fill_free(free, 1.0, sm.Symbol('nope'))
+    np.testing.assert_allclose(prob.time_vector(solution=free, start_time=1.0),
+                               1.0 + 0.25 * np.arange(N))
+    with pytest.raises(ValueError):
+        prob.time_vector()
+    assert prob.bounds == {w.states[0]: (-1.0, 1.0)}
+    assert prob.eom_bounds is None
+
+
 def test_line_search_call_pattern_with_output_ring():
     """IPOPT's line search evaluates g at trial points without asking for
     jac_g there; with ``out_ring=2`` those evaluations do not wait for the
