@@ -387,7 +387,7 @@ int build_tmaps_into(opty_colloc* h, int slot, int seg_first, int seg_count, std
   return OPTY_OK;
 }
 
-int launch_eval(opty_colloc* h) {
+int launch_eval(opty_colloc* h, bool record_events = false) {
   const opty_colloc_cfg& c = h->cfg;
   if (!h->known_set) return fail(OPTY_ERR_STATE, "opty_colloc_set_known must be called before evaluating");
   if (!h->free_valid) return fail(OPTY_ERR_STATE, "no free vector resident on the device");
@@ -404,7 +404,8 @@ int launch_eval(opty_colloc* h) {
       h->jac_inflight = false;
     }
   }
-  RT_CHECK(cudaEventRecord(h->ev0, h->stream));
+  // per-evaluation timing events only on request: every event is one more operation in the stream
+  if (record_events) RT_CHECK(cudaEventRecord(h->ev0, h->stream));
   if (h->inv_dirty && c.num_inv > 0) {
     void* args[2] = {&h->d_uni, &h->d_inv};
     DRV_CHECK(g_drv.LaunchKernel(h->f_inv, 1, 1, 1, 32, 1, 1, 0, (CUstream)h->stream, args, nullptr));
@@ -489,8 +490,10 @@ int launch_eval(opty_colloc* h) {
     h->launches++;
   }
   if (c.const_image_doubles > 0) RT_CHECK(cudaStreamWaitEvent(h->stream, h->ev_repl_done, 0));
-  RT_CHECK(cudaEventRecord(h->ev1, h->stream));
-  h->have_ms = true;
+  if (record_events) {
+    RT_CHECK(cudaEventRecord(h->ev1, h->stream));
+    h->have_ms = true;
+  }
   h->evaluated = true;
   h->con_fetched = h->jac_fetched = false;
   return OPTY_OK;
@@ -819,7 +822,7 @@ int opty_colloc_upload_free(opty_colloc_t* h, const double* free_host) {
 int opty_colloc_eval_device(opty_colloc_t* h, int sync) {
   if (!h) return fail(OPTY_ERR_ARG, "null handle");
   RT_CHECK(cudaSetDevice(h->cfg.device));
-  int rc = launch_eval(h);
+  int rc = launch_eval(h, /*record_events=*/true);
   if (rc) return rc;
   if (sync) RT_CHECK(cudaStreamSynchronize(h->stream));
   return OPTY_OK;
