@@ -152,6 +152,36 @@ def compile_module(source, flags, cache_dir=None, show_compile_output=False,
         return f.read(), cubin_path, False
 
 
+def expression_digest(hasher, expr):
+    """Feeds a canonical, process-independent serialisation of a SymPy
+    expression tree into ``hasher`` (pre-order, explicit stack: the discrete
+    EOM of large models are millions of nodes deep in places).  Symbols and
+    undefined functions contribute their names (and assumptions that change
+    evaluation: none do), numbers their exact value."""
+    import sympy as sm
+    stack = [expr]
+    up = hasher.update
+    while stack:
+        e = stack.pop()
+        if isinstance(e, sm.Symbol):
+            up(b'S' + e.name.encode() + b';')
+        elif isinstance(e, sm.Integer):
+            up(b'I' + str(int(e)).encode() + b';')
+        elif isinstance(e, sm.Rational):
+            up(b'Q' + str(e.p).encode() + b'/' + str(e.q).encode() + b';')
+        elif isinstance(e, sm.Float):
+            up(b'F' + repr(float(e)).encode() + b'@' +
+               str(e._prec).encode() + b';')
+        elif not e.args:
+            up(b'A' + type(e).__name__.encode() + b':' + str(e).encode() +
+               b';')
+        else:
+            name = getattr(getattr(e, 'func', None), '__name__',
+                           type(e).__name__)
+            up(b'(' + name.encode() + b':' + str(len(e.args)).encode() + b';')
+            stack.extend(reversed(e.args))
+
+
 def load_index(cache_dir, input_key):
     path = os.path.join(cache_dir or default_cache_dir(),
                         'index_{}.json'.format(input_key))

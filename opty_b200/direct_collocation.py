@@ -90,6 +90,7 @@ DEFAULT_CUDA_OPTIONS = {
                                 # bound to one group, measured static schedule,
                                 # pre-pass as phase 0 of the same launch
     'persistent_tune': 2,       # re-balancing passes of that schedule
+    'use_index': True,          # set-up cache keyed by the symbolic inputs
     'compile_shards': 'auto',   # modules compiled in parallel (large problems)
     'target_warps': 148 * 16,
     'max_group_cost': 6000.0,
@@ -836,14 +837,95 @@ class _PreparedModule(object):
 
     def __init__(self, col):
         opts = col._cuda_options
+        lo, hi = col._node_range
+        key = self._input_key(col, hi - lo) if opts['use_index'] else None
+        if key is not None and self._load(col, key):
+            return
         logger.info('Lowering and differentiating the constraint function.')
         prog = col._build_program()
         self.program = prog
-        lo, hi = col._node_range
         (self.parts, self.derived, self.source, self.meta, self.cubin,
          self.cubin_path, self.cache_hit) = prepare_program_module(
             prog, hi - lo, col.integration_method, opts, tmp_dir=col.tmp_dir,
             show_compile_output=col.show_compile_output)
+        self.index_hit = False
+        if key is not None and self.cubin_path:
+            build.store_index(col.tmp_dir, key, {
+                'meta': self.meta, 'parts': [list(p) for p in self.parts],
+                'derived': list(self.derived),
+                'cubin': os.path.basename(self.cubin_path),
+                'extra': [os.path.basename(em['cubin_path'])
+                          for em in self.meta.get('extra_modules', ())]})
+
+    # -- set-up cache in front of the symbolic work -------------------------
+    # The reference hashes the generated C *after* CSE, differentiation and
+    # printing, so even a cache hit repeats the symbolic work (opty/utils.py:
+    # 745-770: ~8 s at the 10-link pendulum, minutes at 50 links).  Here the
+    # key is taken from the inputs of that work: the discrete EOM, the symbol
+    # layout, the options and the emitter / skeleton versions.
+    @staticmethod
+    def _input_key(col, num_nodes):
+        import hashlib
+        hasher = hashlib.sha256()
+        rows, uniform, wrt = col._program_inputs()
+        for expr in col.discrete_eom:
+            build.expression_digest(hasher, expr)
+            hasher.update(b'|')
+        hasher.update(repr([[str(a), str(b)] for a, b in rows]).encode())
+        hasher.update(repr([str(u) for u in uniform]).encode())
+        hasher.update(repr([str(w) for w in wrt]).encode())
+        hasher.update(repr([[str(x) for x in rule]
+                            for rule in col._chain_rules()]).encode())
+        opts = {k: v for k, v in col._cuda_options.items()
+                if k not in ('out_ring', 'prefetch_jacobian',
+                             'd2h_skip_constants', 'persistent_tune',
+                             'use_index')}
+        hasher.update(repr(sorted(opts.items())).encode())
+        hasher.update(repr((num_nodes, col.integration_method,
+                            codegen.EMITTER_VERSION, os.cpu_count())).encode())
+        hasher.update(build._header_digest(
+            '#include "colloc_persistent.cuh"').encode())
+        # the lowering / emitter code itself: any change invalidates the index
+        here = os.path.dirname(os.path.abspath(__file__))
+        for name in ('codegen.py', 'ir.py', 'lowering.py', 'program.py',
+                     'direct_collocation.py', 'build.py'):
+            with open(os.path.join(here, name), 'rb') as f:
+                hasher.update(f.read())
+        return hasher.hexdigest()[:32]
+
+    def _load(self, col, key):
+        idx = build.load_index(col.tmp_dir, key)
+        if not idx:
+            return False
+        cache_dir = col.tmp_dir or build.default_cache_dir()
+        paths = [os.path.join(cache_dir, name)
+                 for name in [idx['cubin']] + idx['extra']]
+        if not all(os.path.exists(p) and os.path.getsize(p) for p in paths):
+            return False
+        meta = idx['meta']
+        for em, path in zip(meta.get('extra_modules', ()), paths[1:]):
+            em['cubin_path'] = path
+        self.meta = meta
+        self.parts = [tuple(p) for p in idx['parts']]
+        self.derived = idx['derived']
+        self.source = None
+        self.cubin_path = paths[0]
+        with open(paths[0], 'rb') as f:
+            self.cubin = f.read()
+        self.cache_hit = True
+        self.index_hit = True
+        self.program = _ProgramInfo(meta)
+        logger.info('Skipped lowering and compile, index %s loaded.', key)
+        return True
+
+
+class _ProgramInfo(object):
+    """What the runtime side needs to know about a program whose module came
+    out of the set-up cache (sizes only; the tape was never built)."""
+
+    def __init__(self, meta):
+        self.M, self.P, self.K, self.R = (meta['M'], meta['P'], meta['K'],
+                                          meta['R'])
 
 
 class _CudaEvaluator(object):

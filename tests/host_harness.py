@@ -42,6 +42,7 @@ def _prepare_without_nvcc(collocator):
     real = build.compile_module
     build.compile_module = lambda *a, **k: (b'', '', False)
     try:
+        collocator._cuda_options['use_index'] = False   # the source is needed
         if collocator._cuda_options['groups'] == 'auto':
             collocator._cuda_options['groups'] = 3
         pm = _PreparedModule(collocator)

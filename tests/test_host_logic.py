@@ -385,6 +385,45 @@ def test_module_compiles_for_sm100a_and_is_cached():
         assert 'UTMASTG' not in sass2 and 'UTMALDG' not in sass2
 
 
+def test_setup_index_skips_the_symbolic_work_and_tracks_its_inputs():
+    """The set-up cache is keyed by the inputs of the symbolic work (discrete
+    EOM, symbol layout, options): the same problem comes back from the index
+    without lowering; a changed equation, option or node count does not."""
+    with tempfile.TemporaryDirectory() as tmp:
+        def prepared(w, **opts):
+            col = ConstraintCollocator(*w.collocator_args(),
+                                       **w.collocator_kwargs(), tmp_dir=tmp,
+                                       cuda_options=opts)
+            return col.prepare_module()
+        w = workloads.vyasarayani2011(101, seed=5)
+        first = prepared(w)
+        assert not first.index_hit and first.source
+        again = prepared(workloads.vyasarayani2011(101, seed=5))
+        assert again.index_hit and again.source is None
+        assert again.cubin == first.cubin and again.meta['K'] == first.meta['K']
+        assert again.program.P == first.program.P
+        assert [tuple(p) for p in again.parts] == list(first.parts)
+        # different options, node count or equations: no hit
+        assert not prepared(workloads.vyasarayani2011(101, seed=5),
+                            tile_cols=14).index_hit
+        assert not prepared(workloads.vyasarayani2011(5000)).index_hit
+        w2 = workloads.vyasarayani2011(101, seed=5)
+        w2.eom = w2.eom + sm.Matrix([0, w2.states[0]])
+        other = prepared(w2)
+        assert not other.index_hit and other.cubin != first.cubin
+        # known values are not part of the module: same index entry
+        w3 = workloads.pendulum_swing_up(51)
+        a = prepared(w3)
+        w4 = workloads.pendulum_swing_up(51)
+        for k in w4.known_parameter_map:
+            w4.known_parameter_map[k] *= 2.0
+        b = prepared(w4)
+        assert not a.index_hit and b.index_hit
+        # opting out
+        assert not prepared(workloads.vyasarayani2011(101, seed=5),
+                            use_index=False).index_hit
+
+
 def test_compile_failure_raises_import_error():
     """Build failures surface as ImportError with the compiler's stderr
     (opty/utils.py:909-916, pinned by opty/tests/test_utils.py:333-336)."""
