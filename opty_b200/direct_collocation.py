@@ -853,6 +853,7 @@ class _PreparedModule(object):
             build.store_index(col.tmp_dir, key, {
                 'meta': self.meta, 'parts': [list(p) for p in self.parts],
                 'derived': list(self.derived),
+                'cpu_count': os.cpu_count(),
                 'cubin': os.path.basename(self.cubin_path),
                 'extra': [os.path.basename(em['cubin_path'])
                           for em in self.meta.get('extra_modules', ())]})
@@ -882,7 +883,7 @@ class _PreparedModule(object):
                              'use_index')}
         hasher.update(repr(sorted(opts.items())).encode())
         hasher.update(repr((num_nodes, col.integration_method,
-                            codegen.EMITTER_VERSION, os.cpu_count())).encode())
+                            codegen.EMITTER_VERSION)).encode())
         hasher.update(build._header_digest(
             '#include "colloc_persistent.cuh"').encode())
         # the lowering / emitter code itself: any change invalidates the index
@@ -896,6 +897,11 @@ class _PreparedModule(object):
     def _load(self, col, key):
         idx = build.load_index(col.tmp_dir, key)
         if not idx:
+            return False
+        # the automatic number of parallel compile shards follows the host's
+        # core count: a multi-module entry is only reused on a like host
+        if idx['extra'] and idx.get('cpu_count') != os.cpu_count() and \
+                col._cuda_options['compile_shards'] == 'auto':
             return False
         cache_dir = col.tmp_dir or build.default_cache_dir()
         paths = [os.path.join(cache_dir, name)
