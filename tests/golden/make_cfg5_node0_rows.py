@@ -3,7 +3,7 @@
 ``evalf`` -- independent of the tape / emitter -- and stores them as a golden
 fixture for tools/config5.py / tests."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import sympy as sm

@@ -12,7 +12,7 @@ OPTY_OPTS='{"warps_per_block": 8, ...}' selects kernel options; OPTY_TAG names t
 Checks (the CPU oracle cannot be built for this model in any reasonable time,
 SURVEY.md §8d): residuals of a few equations at node 0 against SymPy
 arbitrary-precision ``evalf`` of the discrete EOM (fixture made by
-tools/config5_reference_rows.py), and the Jacobian against directional finite
+tests/golden/make_cfg5_node0_rows.py), and the Jacobian against directional finite
 differences of the residuals.
 """
 import json
