@@ -81,7 +81,8 @@ typedef struct opty_colloc_cfg {
   int32_t con_tail;         /* extra host slots after the M*(N-1) residuals */
   int32_t jac_tail;         /* extra host slots after the (N-1)*M*P partials */
   int32_t prefetch_jac;     /* opty_colloc_constraints starts the Jacobian D2H speculatively */
-  int32_t persistent;       /* module holds the persistent main kernel: one block per SM bound to one
+  int32_t persistent;       /* != 0: module holds the persistent main kernel (1: block-wide [32*W x C] TMA
+                               tile stores, 2: per-warp [32 x C] stores): one block per SM bound to one
                                group, launched along the schedule of opty_colloc_set_schedule, the
                                pre-pass as phase 0 of the same (cooperative) launch */
   int32_t num_segments;     /* store segments: column runs of the node block written by the group bodies */

@@ -182,7 +182,8 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
                 min_blocks_per_sm=4, tma_load=True, tma_store=True,
                 derived=(), debug_nostore=False, tile_bufs=2, debug_reps=1,
                 const_runs=(), only_groups=None, with_aux=True,
-                persistent=False, tile_major=False):
+                persistent=False, tile_major=False,
+                persistent_block_stores=True):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block;
     a group also owns the residuals of the rows that start inside it).  ``derived`` lists the tape ids
@@ -265,6 +266,8 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         # the base skeleton is used with its per-warp geometry
         w('#define OPTY_WARPS 1')
         w('#define OPTY_PWARPS {}'.format(warps_per_block))
+        if not persistent_block_stores:
+            w('#define OPTY_PERSIST_BLOCK_STORES 0')
         w('#define OPTY_MIN_BLOCKS 1')
     else:
         w('#define OPTY_WARPS {}'.format(warps_per_block))
@@ -513,6 +516,7 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         'tma_store': bool(tma_store),
         'tile_bufs': int(tile_bufs),
         'persistent': bool(persistent),
+        'persistent_block_stores': bool(persistent_block_stores),
         'method': method,
         'entry_kind': prog.entry_kind(),
         'stats': prog.stats(),

@@ -37,6 +37,10 @@ struct OptyPersist {
 // block's range compute the neighbouring block's tile again (same group, same
 // values), so every row of the box is valid; rows beyond the last node are
 // clipped by the tensor map.
+#ifndef OPTY_PERSIST_BLOCK_STORES
+#define OPTY_PERSIST_BLOCK_STORES 1
+#endif
+#if OPTY_PERSIST_BLOCK_STORES
 #undef OPTY_TROW
 #define OPTY_TROW(buf) (ctx.trow0 + (buf) * (OPTY_PWARPS * OPTY_TILE_DOUBLES))
 
@@ -59,6 +63,13 @@ static __device__ __forceinline__ void opty_flush_block(const OptyCtx& ctx) {
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      \
     __syncthreads();                                                                          \
   } while (0)
+#define OPTY_PTILE0(warp) (tiles + (warp) * OPTY_TILE_DOUBLES)
+#define OPTY_PROUND_SYNC() __syncthreads()
+#else
+// per-warp [32 x C] tile stores of the base skeleton (warps run independently)
+#define OPTY_PTILE0(warp) (tiles + (warp) * OPTY_NBUF * OPTY_TILE_DOUBLES)
+#define OPTY_PROUND_SYNC() __syncwarp()
+#endif
 #define OPTY_PSLICE_BYTES OPTY_XSEG_BYTES  // [R+D][34] doubles, 128-byte multiple
 #define OPTY_PSMEM_TILES_BYTES (OPTY_PWARPS * OPTY_NBUF * OPTY_TILE_DOUBLES * 8)
 #define OPTY_PSMEM_BYTES (OPTY_PSMEM_TILES_BYTES + OPTY_PWARPS * OPTY_PSLICE_BYTES + 8 * OPTY_PWARPS + 128)
@@ -113,7 +124,7 @@ static __device__ __forceinline__ void opty_grid_barrier(unsigned int* counter, 
   ctx.ldt = p.ldt;                                                                                \
   ctx.xs = reinterpret_cast<const double*>(slice) + ctx.lane;                                     \
   ctx.ldc = p.ldc;                                                                                \
-  ctx.tile0 = tiles + opty_warp * OPTY_TILE_DOUBLES;                                              \
+  ctx.tile0 = OPTY_PTILE0(opty_warp);                                                             \
   ctx.trow0 = ctx.tile0 + ctx.lane * OPTY_C;                                                      \
   ctx.jac = p.jac;                                                                                \
   ctx.tm = &tm;                                                                                   \
@@ -135,7 +146,7 @@ static __device__ __forceinline__ void opty_grid_barrier(unsigned int* counter, 
     ctx.con = p.con + tile_node0 + ctx.lane;
 
 #define OPTY_PERSIST_LOOP_END()                                                                   \
-    __syncthreads();                                                                              \
+    OPTY_PROUND_SYNC();                                                                           \
   }
 
 #define OPTY_PERSIST_END()                                                                        \

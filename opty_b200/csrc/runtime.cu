@@ -380,7 +380,7 @@ int build_tmaps_into(opty_colloc* h, int slot, int seg_first, int seg_count, std
     for (int g = 0; g < seg_count; ++g) {
       if ((rc = encode_2d(&maps[1 + g], h->d_jac[slot] + c.seg_col0[seg_first + g],
                           (uint64_t)c.seg_ncols[seg_first + g], (uint64_t)h->nn, (uint64_t)h->K * 8,
-                          (uint32_t)c.tile_cols, c.persistent ? 32u * c.warps_per_block : 32u)))
+                          (uint32_t)c.tile_cols, c.persistent == 1 ? 32u * c.warps_per_block : 32u)))
         return rc;
     }
   }

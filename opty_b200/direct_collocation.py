@@ -90,6 +90,8 @@ DEFAULT_CUDA_OPTIONS = {
                                 # bound to one group, measured static schedule,
                                 # pre-pass as phase 0 of the same launch
     'persistent_tune': 2,       # re-balancing passes of that schedule
+    'persistent_block_stores': True,  # one [32*W x C] TMA store per chunk and
+                                # block (False: one [32 x C] store per warp)
     'use_index': True,          # set-up cache keyed by the symbolic inputs
     'compile_shards': 'auto',   # modules compiled in parallel (large problems)
     'target_warps': 148 * 16,
@@ -685,7 +687,8 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         debug_nostore=opts['debug_nostore'],
         tile_bufs=opts['tile_bufs'], debug_reps=opts['debug_reps'],
         const_runs=const_runs, persistent=bool(opts['persistent']),
-        tile_major=bool(opts['tile_major']))
+        tile_major=bool(opts['tile_major']),
+        persistent_block_stores=bool(opts['persistent_block_stores']))
     if opts['persistent']:
         if tma_load != 1 or not tma_store or const_runs:
             raise ValueError('The persistent kernel needs TMA input staging '
@@ -820,7 +823,8 @@ def fill_kernel_config(cfg, meta, opts):
     cfg.tma_store = int(meta['tma_store'])
     cfg.out_ring = int(opts['out_ring'])
     cfg.prefetch_jac = int(bool(opts.get('prefetch_jacobian', False)))
-    cfg.persistent = int(bool(meta.get('persistent', False)))
+    cfg.persistent = (0 if not meta.get('persistent') else
+                      1 if meta.get('persistent_block_stores', True) else 2)
     cfg.num_segments = len(meta['segments'])
     seg_range = meta.get('segment_range', [0, len(meta['segments'])])
     cfg.primary_segments = seg_range[1] - seg_range[0]
