@@ -333,19 +333,38 @@ class CollocationProgram(object):
         cuts_ok = [r for r in range(1, M) if (r * P) % col_align == 0]
         if num_groups == 1 or not cuts_ok:
             return [(0, M)]
-        # cost of a contiguous range counts shared work once per group, so
-        # evaluate ranges directly (M is small)
+        # cost of a contiguous range counts shared work once per group: the
+        # union of the rows' node sets.  Row sets are computed once; a range
+        # is grown row by row from the previous one with the same first row
+        # (the greedy scan below asks for exactly that sequence), so a query
+        # costs the nodes it adds, not a traversal of the tape.  Operation
+        # costs are dyadic numbers: the sums do not depend on the order.
+        op_cost = [ir.OP_COST[o] for o in self.tape.op]
+        row_sets = [frozenset(self.group_nodes([j], stop)) for j in range(M)]
+        row_store = [2.0 * self.row_store_cols(j) for j in range(M)]
         cost_cache = {}
+        chain = {}      # first row -> (end row, node set, node cost, stores)
 
         def rng_cost(r0, r1):
             key = (r0, r1)
             c = cost_cache.get(key)
-            if c is None:
-                c = (self.tape.cost(self.group_nodes(range(r0, r1), stop)) +
-                     2.0 * sum(self.row_store_cols(j)
-                               for j in range(r0, r1)))
-                cost_cache[key] = c
-            return c
+            if c is not None:
+                return c
+            state = chain.get(r0)
+            if state is None or state[0] > r1:
+                state = (r0, set(), 0.0, 0.0)
+            end, nodes, ncost, stores = state
+            if end == r0 and not nodes:
+                nodes = set()
+            while end < r1:
+                new = row_sets[end] - nodes
+                ncost += sum(op_cost[i] for i in new)
+                nodes |= new
+                stores += row_store[end]
+                end += 1
+                cost_cache[(r0, end)] = ncost + stores
+            chain[r0] = (end, nodes, ncost, stores)
+            return cost_cache[key]
 
         # minimise the maximum group cost: binary search on the bound with a
         # greedy feasibility check
