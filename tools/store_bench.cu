@@ -137,20 +137,16 @@ int main() {
   // (4 blocks x 2 warps per SM = 56 KB of shared memory per block)?
   const int F = 56 * 1024;
   std::vector<Variant> vs = {
-      {"tma store only              C30 occ8", 0, 1012, 1012, 30, 2, 2, 0, 8, F},
-      {"tma store only              C30 occ-free", 0, 1012, 1012, 30, 2, 2, 0, 8, 0},
-      {"compute only w250           C30 occ8", 6, 1012, 1012, 30, 2, 2, 250, 8, F},
-      {"tma store+compute w250      C30 occ8", 0, 1012, 1012, 30, 2, 2, 250, 8, F},
-      {"compute only w500           C30 occ8", 6, 1012, 1012, 30, 2, 2, 500, 8, F},
-      {"tma store+compute w500      C30 occ8", 0, 1012, 1012, 30, 2, 2, 500, 8, F},
-      {"compute only w1000          C30 occ8", 6, 1012, 1012, 30, 2, 2, 1000, 8, F},
-      {"tma store+compute w1000     C30 occ8", 0, 1012, 1012, 30, 2, 2, 1000, 8, F},
-      {"tma store only              C62 occ8", 0, 1012, 1012, 62, 2, 2, 0, 8, F},
-      {"compute only w1000          C62 occ8", 6, 1012, 1012, 62, 2, 2, 1000, 8, F},
-      {"tma store+compute w1000     C62 occ8", 0, 1012, 1012, 62, 2, 2, 1000, 8, F},
-      {"tma store+compute w1000 B4  C30 occ8", 0, 1012, 1012, 30, 2, 4, 1000, 8, F},
-      {"tma store only  W1          C30 occ8", 0, 1012, 1012, 30, 1, 2, 0, 8, 28 * 1024},
-      {"tma store+compute w500 W1   C30 occ8", 0, 1012, 1012, 30, 1, 2, 500, 8, 28 * 1024},
+      // does a 128-byte aligned row pitch (1024 columns instead of 1012) raise the store floor?
+      {"tma store only  pitch 1012  C30 occ8", 0, 1012, 1012, 30, 2, 2, 0, 8, F},
+      {"tma store only  pitch 1024  C30 occ8", 0, 1012, 1024, 30, 2, 2, 0, 8, F},
+      {"tma store only  pitch 1012  C62 occ8", 0, 1012, 1012, 62, 2, 2, 0, 8, F},
+      {"tma store only  pitch 1024  C62 occ8", 0, 1012, 1024, 62, 2, 2, 0, 8, F},
+      {"tma store only  pitch 1024  C16 swizzled occ8", 1, 1012, 1024, 16, 2, 2, 0, 8, F},
+      {"tma store only  pitch 1024  C46 occ8", 0, 1012, 1024, 46, 2, 2, 0, 8, F},
+      {"tma store only  pitch 1012  C46 occ8", 0, 1012, 1012, 46, 2, 2, 0, 8, F},
+      {"tma store+compute w250 pitch 1024 C30 occ8", 0, 1012, 1024, 30, 2, 2, 250, 8, F},
+      {"tma store+compute w250 pitch 1012 C30 occ8", 0, 1012, 1012, 30, 2, 2, 250, 8, F},
   };
 
   for (const Variant& v : vs) {
