@@ -385,6 +385,44 @@ def test_module_compiles_for_sm100a_and_is_cached():
         assert 'UTMASTG' not in sass2 and 'UTMALDG' not in sass2
 
 
+def test_persistent_and_sharded_modules_compile_for_sm100a():
+    """Compile-only checks (no GPU): the persistent variant carries the TMA
+    paths and its grid barrier; a sharded build yields one module per group
+    range and only the first one holds the auxiliary kernels."""
+    w = workloads.n_link_pendulum(10, 40, seed=7)
+    with tempfile.TemporaryDirectory() as tmp:
+        col = ConstraintCollocator(
+            *w.collocator_args(), **w.collocator_kwargs(), tmp_dir=tmp,
+            cuda_options={'persistent': True, 'groups': 4,
+                          'warps_per_block': 4, 'min_blocks_per_sm': 1})
+        pm = col.prepare_module()
+        assert pm.meta['persistent'] and not pm.meta['extra_modules']
+        sass = subprocess.run(['cuobjdump', '-sass', pm.cubin_path],
+                              capture_output=True, text=True).stdout
+        assert 'UTMALDG' in sass and 'UTMASTG' in sass
+        assert 'ATOM' in sass or 'RED' in sass       # grid barrier arrive
+        assert 'OptyPersist ps' in pm.source
+
+        col = ConstraintCollocator(
+            *w.collocator_args(), **w.collocator_kwargs(), tmp_dir=tmp,
+            cuda_options={'groups': 6, 'compile_shards': 3})
+        pm = col.prepare_module()
+        extra = pm.meta['extra_modules']
+        assert len(extra) == 2
+        ranges = [pm.meta['group_range']] + [e['group_range'] for e in extra]
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(pm.parts)
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        segs = [pm.meta['segment_range']] + [e['segment_range']
+                                             for e in extra]
+        assert segs[0][0] == 0 and segs[-1][1] == len(pm.meta['segments'])
+        for e in extra:
+            syms = subprocess.run(['cuobjdump', '-elf', e['cubin_path']],
+                                  capture_output=True, text=True).stdout
+            assert 'opty_colloc_eval' in syms
+            assert 'opty_colloc_pre' not in syms
+            assert 'opty_colloc_inv' not in syms
+
+
 def test_setup_index_skips_the_symbolic_work_and_tracks_its_inputs():
     """The set-up cache is keyed by the inputs of the symbolic work (discrete
     EOM, symbol layout, options): the same problem comes back from the index
