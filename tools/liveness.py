@@ -21,7 +21,16 @@ for j in (prog.M // 2 + 1, prog.M - 1):
     def rec(i, emit=emit, order=order):
         order.append(i); emit(i)
     bw._emit = rec
-    outs = [prog.con[j]] + list(prog.jac[j])
+    n = prog.M          # states (square systems: n = M)
+    cols = list(range(P))
+    if len(sys.argv) > 2 and sys.argv[2] == 'bylink':
+        # partials with respect to the same state (current / next value) together
+        half = n // 2
+        cols = []
+        for k in range(half):
+            cols += [k, n + k, half + k, n + half + k]
+        cols += [c for c in range(P) if c not in cols]
+    outs = [prog.con[j]] + [prog.jac[j][c] for c in cols]
     for o in outs:
         bw.need(o)
     pos = {nid: k for k, nid in enumerate(order)}
