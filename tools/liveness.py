@@ -33,6 +33,10 @@ for j in (prog.M // 2 + 1, prog.M - 1):
     outs = [prog.con[j]] + [prog.jac[j][c] for c in cols]
     for o in outs:
         bw.need(o)
+    if len(sys.argv) > 2 and sys.argv[2] == 'tapeorder':
+        # operation-major: nodes in creation order of the tape (forward mode
+        # creates the tangent nodes of an operation right after it)
+        order = sorted(order)
     pos = {nid: k for k, nid in enumerate(order)}
     last = {}
     for k, nid in enumerate(order):
