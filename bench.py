@@ -127,27 +127,64 @@ def algorithmic_bytes(n, q, k, r, s, M, P, N_cols, nodes):
 
 
 # ---------------------------------------------------------------------------
+# CPU arms.  The reference's own implementation (baseline/_ref, installed
+# unmodified with pip --target; see baseline/reference.py) is what is timed:
+# ``ConstraintCollocator(backend='cython', parallel=True)`` with the
+# protocol of BASELINE.md §3.  Only if it cannot be imported does the oracle
+# port (oracle/opty_oracle.py, bit-identical results) take its place.
+# ---------------------------------------------------------------------------
+def _cpu_callables(parallel, threads):
+    """Returns ``(con, jac, num_free, workload, kind, effective_threads)``
+    for BASELINE configs[1] on the host cores."""
+    from baseline import reference as ref
+    threads = ref.prepare_environment(threads)
+    w = build_workload(1)
+    if ref.available():
+        try:
+            col = ref.collocator(w, parallel)
+            con = col.generate_constraint_function()
+            jac = col.generate_jacobian_function()
+            eff = ref.omp_max_threads() if parallel else 1
+            return con, jac, col.num_free, w, 'reference', eff or threads
+        except Exception as err:  # pragma: no cover - depends on the host
+            sys.stderr.write('reference import/build failed ({}: {}); using '
+                             'the oracle port\n'.format(
+                                 type(err).__name__, err))
+    from oracle.opty_oracle import OracleCollocator
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs(),
+                           parallel=parallel)
+    eff = ref.omp_max_threads() if parallel else 1
+    return (orc.constraints, lambda f: orc.jacobian(f, copy=False),
+            orc.num_free, w, 'port', eff or threads)
+
+
+def _time_cpu_evals(con, jac, frees, steps, warmup):
+    for i in range(max(warmup, 1)):
+        con(frees[i % 2])
+        jac(frees[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        con(frees[i % 2])
+        jac(frees[i % 2])
+    return time.perf_counter() - t0
+
+
 def run_reference_arm(args, rank, world):
-    """The reference's CPU path (oracle port, all host threads)."""
+    """The reference's CPU path with every host thread it can use; rank 0
+    only (the other ranks exit without work)."""
     if rank != 0:
         return
-    from oracle.opty_oracle import OracleCollocator
-    w = build_workload(1)
-    threads = os.cpu_count() or 1
-    os.environ.setdefault('OMP_NUM_THREADS', str(threads))
-    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs(),
-                           parallel=True)
-    free = w.free(orc.num_free)
+    from baseline import reference as ref
+    threads = ref.host_threads()
+    con, jac, num_free, w, kind, eff = _cpu_callables(True, threads)
+    free = w.free(num_free)
     frees = [free, free + 1e-3]
-    for i in range(max(args.warmup, 1)):
-        orc.constraints(frees[i % 2])
-        orc.jacobian(frees[i % 2])
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        orc.constraints(frees[i % 2])
-        orc.jacobian(frees[i % 2])
-    dt = time.perf_counter() - t0
+    dt = _time_cpu_evals(con, jac, frees, args.steps, args.warmup)
     value = args.steps / dt
+    what = ("the unmodified reference (baseline/_ref): ConstraintCollocator("
+            "backend='cython', parallel=True), generated C + Cython prange "
+            "loop" if kind == 'reference' else
+            'oracle port of the generated C + node loop (gcc -O2 -fopenmp)')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -155,11 +192,13 @@ def run_reference_arm(args, rank, world):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD,
-                   'note': 'CPU only: reference algorithm (oracle port of '
-                           'the generated C + node loop, gcc -O2 -fopenmp), '
-                           'one full 10k-node eval per step'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads,
-                         'kind': 'port',
+                   'note': 'CPU only: {}; one full 10k-node eval '
+                           '(constraints + jacobian at a new point) per '
+                           'step'.format(what)},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': eff,
+                         'kind': kind,
+                         'omp_num_threads': os.environ.get('OMP_NUM_THREADS'),
+                         'host_threads': threads,
                          'sample': '{} full evals (constraints + jacobian) '
                                    'of the 10k-node workload'.format(
                                        args.steps)},
@@ -169,35 +208,71 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(budget_s=12.0):
-    """Oracle timed on the host cores: serial and OpenMP."""
-    from oracle.opty_oracle import OracleCollocator
-    w = build_workload(1)
+def cpu_baseline(budget_s=16.0):
+    """The reference (or, failing that, the oracle port) timed on the host
+    cores of the GPU box in the same run: OpenMP on all threads and serial.
+    Runs in a child process so that OMP_NUM_THREADS is set before libgomp is
+    loaded, whatever the parent process has already imported."""
+    code = ('import json, sys; sys.path.insert(0, {root!r}); import bench; '
+            'print(json.dumps(bench._cpu_baseline_child({budget!r})))'
+            .format(root=ROOT, budget=budget_s))
+    env = dict(os.environ)
+    env.pop('OMP_NUM_THREADS', None)
+    proc = subprocess.run([sys.executable, '-c', code], capture_output=True,
+                          text=True, env=env, cwd=ROOT)
+    for ln in reversed(proc.stdout.strip().splitlines()):
+        try:
+            return json.loads(ln)
+        except ValueError:
+            continue
+    return {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'failed',
+            'sample': (proc.stderr or 'no output')[-400:]}
+
+
+def _cpu_baseline_child(budget_s):
+    from baseline import reference as ref
+    threads = ref.host_threads()
     out = {}
-    threads = os.cpu_count() or 1
-    for label, par in (('serial', False), ('parallel', True)):
-        orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs(),
-                               parallel=par)
-        free = w.free(orc.num_free)
-        orc.constraints(free)
-        orc.jacobian(free)
-        count = 0
-        t0 = time.perf_counter()
+    kind = eff = None
+    for label, par in (('parallel', True), ('serial', False)):
+        con, jac, num_free, w, kind_, eff_ = _cpu_callables(par, threads)
+        if par:
+            kind, eff = kind_, eff_
+        free = w.free(num_free)
+        frees = [free, free + 1e-3]
+        _time_cpu_evals(con, jac, frees, 0, 2)
+        times = []
+        t_start = time.perf_counter()
         while True:
-            orc.constraints(free)
-            orc.jacobian(free)
-            count += 1
-            dt = time.perf_counter() - t0
-            if dt > budget_s / 2 or count >= 200:
+            f = frees[len(times) % 2]
+            t0 = time.perf_counter()
+            con(f)
+            t1 = time.perf_counter()
+            jac(f)
+            t2 = time.perf_counter()
+            times.append((t1 - t0, t2 - t1))
+            if time.perf_counter() - t_start > budget_s / 2 or \
+                    len(times) >= 400:
                 break
-        out[label] = (count / dt, count)
-    return {'value': out['parallel'][0], 'unit': UNIT, 'cores': threads,
-            'kind': 'port',
-            'sample': '{} full evals of the 10k-node workload with OpenMP on '
-                      '{} threads (serial, 1 core: {:.2f} evals/s over {} '
-                      'evals)'.format(out['parallel'][1], threads,
-                                      out['serial'][0], out['serial'][1]),
-            'serial_value': out['serial'][0]}
+        tc = np.array([t[0] for t in times])
+        tj = np.array([t[1] for t in times])
+        out[label] = {
+            'evals': len(times),
+            'evals_per_s': len(times) / float(tc.sum() + tj.sum()),
+            'constraints_ms_best': 1e3 * float(tc.min()),
+            'constraints_ms_median': 1e3 * float(np.median(tc)),
+            'jacobian_ms_best': 1e3 * float(tj.min()),
+            'jacobian_ms_median': 1e3 * float(np.median(tj))}
+    par = out['parallel']
+    return {'value': par['evals_per_s'], 'unit': UNIT, 'cores': eff,
+            'kind': kind, 'host_threads': threads,
+            'sample': '{} full evals of the 10k-node workload, '
+                      "backend='cython', parallel=True on {} OpenMP threads "
+                      '(serial, 1 core: {:.2f} evals/s over {} evals)'.format(
+                          par['evals'], eff, out['serial']['evals_per_s'],
+                          out['serial']['evals']),
+            'serial_value': out['serial']['evals_per_s'],
+            'detail': out}
 
 
 def run_own_arm(args, rank, world, local_rank):

@@ -503,15 +503,19 @@ class OracleCollocator(object):
             out = np.hstack((out, self._instance_values(free)))
         return out
 
-    def jacobian(self, free):
+    def jacobian(self, free, copy=True):
         """Node-major partials then the instance entries
-        (direct_collocation.py:2885-2887, 2985-2991)."""
+        (direct_collocation.py:2885-2887, 2985-2991).  With ``copy=False``
+        and no instance constraints the result is a view of the persistent
+        buffer, overwritten by the next call -- exactly what the reference
+        returns (direct_collocation.py:2814, 2887); the default copies so
+        that tests can hold several results."""
         free = np.asarray(free, dtype=float)
         jac_loop = self._jacobian_loop()
         vals = jac_loop(self._jac_buffer, *self._numeric_args(free)).ravel()
         if self.o:
             return np.hstack((vals, self._instance_jacobian_values(free)))
-        return vals.copy()
+        return vals.copy() if copy else vals
 
     # -- COO structure: the reference's per-node loop -------------------------
     def jacobian_indices(self):
