@@ -385,8 +385,12 @@ def run_own_arm(args, rank, world, local_rank):
                     world),
                 'groups': ev.meta['num_groups'],
                 'tile_cols': ev.meta['C'],
+                'tile_bufs': ev.meta['tile_bufs'],
+                'warps_per_block': ev.meta['warps_per_block'],
+                'min_blocks_per_sm': ev.meta['min_blocks_per_sm'],
                 'tma_load': ev.meta['tma_load'],
                 'tma_store': ev.meta['tma_store'],
+                'schedule': ev.meta['schedule'],
                 'l2': 'rotating {} device output sets ({:.0f} MB) > 126 MB '
                       'L2'.format(OUT_RING, OUT_RING * 8e-6 * (
                           prog.M * nn + nn * prog.K)),

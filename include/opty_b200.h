@@ -15,12 +15,18 @@
  *     `_merge_fixed_free` (opty/direct_collocation.py:2891-2926), the slicing
  *     and result allocation in `constraints` (opty/direct_collocation.py:
  *     2382-2446) and `constraints_jacobian` (opty/direct_collocation.py:
- *     2816-2887), and the index loop of `jacobian_indices`
- *     (opty/direct_collocation.py:2628-2684).
+ *     2816-2887), the index loop of `jacobian_indices`
+ *     (opty/direct_collocation.py:2628-2684), and the quadrature of
+ *     `create_objective_function` (opty/utils.py:329-470).
  *
  * Plain pointers and sizes only.  All values are IEEE float64, all indices
  * int64.  Every function returns 0 on success and a negative code on failure;
  * `opty_colloc_last_error()` then describes the failure (thread local).
+ *
+ * The configuration holds the PROBLEM in the reference's notation only.  The
+ * kernel geometry (block size, staging tiles, tensor-map shapes ...) is a
+ * property of the generated module and is read from the module itself (its
+ * `opty_module_info` table); it does not cross this boundary.
  *
  * A handle is NOT reentrant (the reference's persistent Jacobian buffer,
  * opty/direct_collocation.py:2814, makes its `jacobian()` non-reentrant too).
@@ -35,9 +41,8 @@
 extern "C" {
 #endif
 
-#define OPTY_B200_ABI_VERSION 6
+#define OPTY_B200_ABI_VERSION 7
 #define OPTY_MAX_GROUPS 1024
-#define OPTY_MAX_SEGMENTS 1024
 
 #define OPTY_OK 0
 #define OPTY_ERR_ARG -1     /* invalid argument / configuration */
@@ -50,50 +55,22 @@ extern "C" {
  * (returned through opty_colloc_jacobian), no residuals, no neighbour column. */
 enum { OPTY_BACKWARD_EULER = 0, OPTY_MIDPOINT = 1, OPTY_ELEMENTWISE = 2 };
 
-/* Problem + kernel geometry.  Symbols follow the reference's notation
- * (opty/direct_collocation.py:101-114). */
+/* The problem, in the reference's notation (opty/direct_collocation.py:101-114). */
 typedef struct opty_colloc_cfg {
-  int32_t abi_version;      /* OPTY_B200_ABI_VERSION */
-  int32_t device;           /* CUDA device ordinal */
-  int32_t N;                /* collocation nodes of the whole problem */
-  int32_t node_lo;          /* this handle evaluates constraint nodes */
-  int32_t node_hi;          /*   [node_lo, node_hi) of the N-1 (a shard) */
-  int32_t n;                /* states */
-  int32_t q;                /* unknown input trajectories */
-  int32_t k;                /* known input trajectories */
-  int32_t r;                /* unknown parameters */
-  int32_t s;                /* 1 if the node time interval is free, else 0 */
-  int32_t pk;               /* known parameters */
-  int32_t M;                /* equations of motion */
-  int32_t P;                /* partials per equation (2n+q+r+s or 2n+2q+r+s) */
-  int32_t method;           /* OPTY_BACKWARD_EULER / OPTY_MIDPOINT */
-  int32_t num_inv;          /* entries of the node-invariant table */
-  int32_t num_groups;       /* output groups */
-  int32_t num_derived;      /* D: derived rows written by the pre-pass kernel */
-  int32_t tile_cols;        /* C: columns of the Jacobian staging tile */
-  int32_t warps_per_block;
-  int32_t pre_groups;       /* grid.y of the pre-pass kernel (groups of derived rows) */
-  int32_t tile_bufs;        /* staging tiles per warp (1..4) */
-  int32_t tma_load;         /* input staging of the module: 1 TMA tile loads, 0 plain loads into shared
-                               memory, 2 none (lanes read the trajectory matrix directly) */
-  int32_t tma_store;        /* module was emitted with TMA Jacobian stores */
-  int32_t out_ring;         /* number of device output sets to rotate (>=1) */
-  int32_t con_tail;         /* extra host slots after the M*(N-1) residuals */
-  int32_t jac_tail;         /* extra host slots after the (N-1)*M*P partials */
-  int32_t prefetch_jac;     /* opty_colloc_constraints starts the Jacobian D2H speculatively */
-  int32_t persistent;       /* != 0: module holds the persistent main kernel (1: block-wide [32*W x C] TMA
-                               tile stores, 2: per-warp [32 x C] stores): one block per SM bound to one
-                               group, launched along the schedule of opty_colloc_set_schedule, the
-                               pre-pass as phase 0 of the same (cooperative) launch */
-  int32_t num_segments;     /* store segments: column runs of the node block written by the group bodies */
-  int32_t primary_segments; /* segments [0, primary_segments) belong to the module given to
-                               opty_colloc_create; the rest to modules added with opty_colloc_add_module */
-  int32_t const_image_doubles; /* total length of the constant column runs that the pre-pass kernel
-                                  replicates into every node row (0: none); segments and constant
-                                  runs together tile the M*P columns */
-  int32_t seg_col0[OPTY_MAX_SEGMENTS];   /* first Jacobian column of segment s */
-  int32_t seg_ncols[OPTY_MAX_SEGMENTS];  /* number of columns of segment s */
-  double h;                 /* fixed node time interval (ignored when s=1) */
+  int32_t abi_version;   /* OPTY_B200_ABI_VERSION */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t N;             /* collocation nodes of the whole problem */
+  int32_t node_lo;       /* this handle evaluates constraint nodes */
+  int32_t node_hi;       /*   [node_lo, node_hi) of the N-1 (a shard) */
+  int32_t n, q, k;       /* states, unknown / known input trajectories */
+  int32_t r, s, pk;      /* unknown parameters, 1 if h is free, known parameters */
+  int32_t M, P;          /* equations of motion, partials per equation */
+  int32_t method;        /* OPTY_BACKWARD_EULER / OPTY_MIDPOINT / OPTY_ELEMENTWISE */
+  int32_t out_ring;      /* device output sets to rotate through (>= 1) */
+  int32_t prefetch_jac;  /* opty_colloc_constraints starts the Jacobian D2H speculatively */
+  int32_t con_tail;      /* extra host slots after the M*(N-1) residuals (instance constraints) */
+  int32_t jac_tail;      /* extra host slots after the (N-1)*M*P partials */
+  double h;              /* fixed node time interval (ignored when s = 1) */
 } opty_colloc_cfg;
 
 typedef struct opty_colloc opty_colloc_t;
@@ -107,12 +84,19 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
 
 int opty_colloc_destroy(opty_colloc_t* h);
 
+/* Problems too large for one nvcc run are compiled as several modules
+ * (contiguous ranges of output groups) in parallel -- the reference compiles
+ * its single generated C function serially (opty/utils.py:866-907).  Adds one
+ * of them; all must be added before the first evaluation.  The module given
+ * to opty_colloc_create carries the invariants and pre-pass kernels. */
+int opty_colloc_add_module(opty_colloc_t* h, const void* cubin, size_t cubin_bytes);
+
 /* Known input trajectories `traj` as [k][N] (row-major, full problem length N)
  * and known parameter values `params` [pk], in the collocator's symbol order.
  * Replaces the known-value half of `_merge_fixed_free`
  * (opty/direct_collocation.py:2911-2926).  Must be called once before the
- * first evaluation (also when k = pk = 0) and again whenever a known
- * trajectory changes. */
+ * first evaluation (also when k = pk = 0) and again whenever a known value
+ * changes. */
 int opty_colloc_set_known(opty_colloc_t* h, const double* traj, const double* params);
 
 /* Copies the free vector (length n*N + q*N + r + s, layout of
@@ -135,6 +119,26 @@ int opty_colloc_constraints(opty_colloc_t* h, const double* free_host, double* c
  * the (node_hi-node_lo)*M*P partials, node-major. */
 int opty_colloc_jacobian(opty_colloc_t* h, const double* free_host, double* jac_host);
 
+/* Several handles (one per GPU, each a shard of the constraint nodes) driven
+ * by ONE host thread: `begin` uploads, launches and queues the device->host
+ * copies of what is asked for without waiting, `finish` waits.  With
+ * opty_colloc_set_host_outputs every handle writes straight into its slice of
+ * one full-problem host vector: the node-major Jacobian block of a shard is
+ * contiguous (opty/direct_collocation.py:2681-2684), its residuals are M
+ * strided segments of the eom-major vector (opty/direct_collocation.py:2446). */
+int opty_colloc_begin(opty_colloc_t* h, const double* free_host, int want_con, int want_jac);
+int opty_colloc_finish(opty_colloc_t* h);
+
+/* Full-problem host vectors (from opty_host_alloc) that this handle's
+ * device->host copies target instead of its own pinned buffers: residuals
+ * M*(N-1) (+ tail), Jacobian (N-1)*M*P (+ tail).  NULL, NULL restores the
+ * handle's own buffers.  Speculative Jacobian copies are off in this mode. */
+int opty_colloc_set_host_outputs(opty_colloc_t* h, double* con_full, double* jac_full);
+
+/* Page-locked host memory usable from every device (cudaHostAllocPortable). */
+int opty_host_alloc(size_t bytes, void** ptr);
+int opty_host_free(void* ptr);
+
 /* Pinned host buffers owned by the handle: the free-vector staging buffer,
  * the residual buffer (M*nodes + con_tail) and the Jacobian buffer
  * (nodes*M*P + jac_tail).  Valid until opty_colloc_destroy. */
@@ -149,46 +153,33 @@ int opty_colloc_device_buffers(opty_colloc_t* h, void** traj, int64_t* ldt, void
 /* Restricts Jacobian device->host copies to the column ranges
  * [col_begin[i], col_end[i]) of every node block.  Columns outside the ranges
  * must hold values that do not change between calls (literals, or functions
- * of known parameters only); they reach the pinned Jacobian buffer through
- * one full copy after this call / after opty_colloc_set_known (or from
- * `fill`, a K-entry per-node pattern, if given).  `num_ranges` = 0 restores
- * full copies. */
+ * of known parameters only); they reach the host Jacobian buffer through one
+ * full copy after this call / after opty_colloc_set_known /
+ * opty_colloc_invalidate_host_jacobian.  `num_ranges` = 0 restores full
+ * copies. */
 int opty_colloc_set_d2h_columns(opty_colloc_t* h, int num_ranges, const int32_t* col_begin,
-                                const int32_t* col_end, const double* fill);
+                                const int32_t* col_end);
 
-/* Problems too large for one nvcc run are compiled as several modules (contiguous
- * ranges of output groups) in parallel -- the reference compiles its single
- * generated C function serially (opty/utils.py:866-907).  Adds the module that
- * writes store segments [seg_first, seg_first + seg_count) with `num_groups`
- * output groups; modules are added in segment order and all of them before the
- * first evaluation.  The module given to opty_colloc_create carries the
- * invariants and pre-pass kernels. */
-int opty_colloc_add_module(opty_colloc_t* h, const void* cubin, size_t cubin_bytes, int seg_first,
-                           int seg_count, int num_groups);
+/* The next Jacobian fetch copies every column again (for consumers that
+ * modified the returned buffer in place). */
+int opty_colloc_invalidate_host_jacobian(opty_colloc_t* h);
 
-/* Persistent main kernel only: the block -> work table, one (group, first tile,
- * end tile) triple per block (group = index inside the module, tiles of 32
- * nodes); every (group, tile) pair must be covered exactly once and there may
- * be at most one block per SM.  Replaces the `prange` node loop's static
- * OpenMP schedule (opty/utils.py:716-741) with a measured one. */
-int opty_colloc_set_schedule(opty_colloc_t* h, int num_blocks, const int32_t* triples);
+/* Quadrature of a running cost over the node grid, the numeric half of
+ * `create_objective_function` (opty/utils.py:329-470): the handle (created
+ * with method = OPTY_ELEMENTWISE from a module that evaluates the integrand
+ * in column 0 and its partials with respect to the n array arguments in
+ * columns 1..n at every node) returns
+ *     value = scale * sum_i w_i * integrand(node i)
+ *     grad[a*N + i] = scale * w_i * d integrand / d arg_a (node i)
+ * with backward-Euler weights w_0 = 0, w_i = 1 (opty/utils.py:418-423) or
+ * midpoint weights (method = OPTY_MIDPOINT: the integrand module is then
+ * evaluated at the N-1 midpoints, opty/utils.py:424-434).  `grad` has n*N
+ * entries. */
+int opty_colloc_quadrature(opty_colloc_t* h, const double* free_host, double scale, int rule,
+                           double* value, double* grad);
 
-/* clock64 ticks every block of the last persistent launch spent in its group
- * phase (input for re-balancing the schedule). */
-int opty_colloc_block_clocks(opty_colloc_t* h, int num_blocks, int64_t* clocks);
-
-/* Registers the constant column runs of the node block (cfg.const_image_doubles
- * columns in total): run i covers columns [col0[i], col0[i]+len[i]) (even start
- * and length); `lit` / `inv_idx` give, in run order, each column's literal value
- * or (inv_idx >= 0) its index in the node-invariant table.  These are the
- * entries the reference recomputes for every node although they do not depend
- * on it (opty/utils.py:483-494 evaluates the full matrix per node); here one
- * image is replicated into all node rows by TMA tile stores.  Must be called
- * once after opty_colloc_create when cfg.const_image_doubles > 0. */
-int opty_colloc_set_const_runs(opty_colloc_t* h, int num_runs, const int32_t* col0, const int32_t* len,
-                               const double* lit, const int32_t* inv_idx);
-
-/* CUDA-event duration (ms) of the kernels of the last evaluation. */
+/* CUDA-event duration (ms) of the kernels of the last evaluation started with
+ * opty_colloc_eval_device. */
 int opty_colloc_last_kernel_ms(opty_colloc_t* h, float* ms);
 
 /* Measurement aid: launches `steps` device-resident evaluations back to back

@@ -53,11 +53,18 @@ def build_runtime(force=False, verbose=False):
             os.path.join(INCLUDE_DIR, 'opty_b200.h')]
     if not force and not _newer(deps, RUNTIME_LIB):
         return RUNTIME_LIB
+    tmp_lib = '{}.{}.tmp'.format(RUNTIME_LIB, os.getpid())
     cmd = [nvcc_path()] + ARCH_FLAGS + [
         '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC',
-        '-cudart', 'static', '-o', RUNTIME_LIB, RUNTIME_SRC]
+        '-cudart', 'static', '-o', tmp_lib, RUNTIME_SRC, '-ldl']
     logger.info('Building %s', RUNTIME_LIB)
     proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode == 0:
+        # several processes (one per GPU) may build at once on a cold tree:
+        # nobody ever sees a half-written library
+        os.replace(tmp_lib, RUNTIME_LIB)
+    elif os.path.exists(tmp_lib):
+        os.remove(tmp_lib)
     if verbose:
         print(proc.stdout)
         print(proc.stderr)
@@ -70,12 +77,7 @@ def build_runtime(force=False, verbose=False):
 
 def _header_digest(source=''):
     hasher = hashlib.sha256()
-    names = ['colloc_kernel.cuh', 'colloc_params.h']
-    # optional skeleton pieces only count for the modules that include them
-    for extra in ('colloc_persistent.cuh',):
-        if '#include "{}"'.format(extra) in source:
-            names.append(extra)
-    for name in names:
+    for name in ('colloc_kernel.cuh', 'colloc_params.h'):
         with open(os.path.join(CSRC, name), 'rb') as f:
             hasher.update(f.read())
     return hasher.hexdigest()
@@ -112,9 +114,19 @@ def compile_module(source, flags, cache_dir=None, show_compile_output=False,
             return f.read(), cubin_path, True
 
     src_path = os.path.join(cache_dir, 'colloc_{}.cu'.format(key))
-    with open(src_path, 'w') as f:
-        f.write('// opty_code_hash={}\n'.format(key))
-        f.write(source)
+    text = '// opty_code_hash={}\n'.format(key) + source
+    try:
+        with open(src_path) as f:
+            same = f.read() == text
+    except OSError:
+        same = False
+    if not same:
+        # written under a private name first: another rank compiling the same
+        # module must never read a truncated source
+        tmp_src = '{}.{}.tmp'.format(src_path, os.getpid())
+        with open(tmp_src, 'w') as f:
+            f.write(text)
+        os.replace(tmp_src, src_path)
     tmp_out = tempfile.NamedTemporaryFile(
         dir=cache_dir, suffix='.cubin.tmp', delete=False)
     tmp_out.close()

@@ -17,27 +17,52 @@ contains
     trajectory matrix,
 
 ``opty_colloc_eval``
-    the hot kernel, persistent: one block slot per SM x ``min_blocks``.  A
-    warp owns 32 consecutive collocation nodes (lane = node) of one output
-    group (a contiguous range of EOM rows) per tile; it stages the tile's
-    slice of the trajectory matrix in shared memory with TMA tile loads, runs
-    the group's straight-line float64 code, writes the residuals eom-major and
-    streams the node-major Jacobian block through a double-buffered
-    shared-memory tile that is drained by TMA tile stores.
+    the hot kernel: grid = (node tiles, output groups).  A warp owns 32
+    consecutive collocation nodes (lane = node) of one output group (a
+    contiguous range of EOM rows); the block stages the tile's slice of the
+    trajectory matrix in shared memory with TMA tile loads, every warp runs
+    the group's straight-line float64 code -- ordered by the register-pressure
+    scheduler of :mod:`opty_b200.schedule` --, writes the residuals eom-major
+    and streams the node-major Jacobian block through per-warp shared-memory
+    staging buffers that are drained by TMA tile stores, one *phase* (a few
+    column runs of one equation) at a time,
 
-The skeleton (staging, tiles, TMA, flush) is hand written in
+``opty_module_info``
+    the kernel geometry as a table of integers that the host runtime reads
+    from the loaded module, so that no tuning parameter crosses the C-ABI.
+
+The skeleton (staging, buffers, TMA, flush) is hand written in
 ``csrc/colloc_kernel.cuh``; only the arithmetic bodies and sizes come from
 here.
 """
 
 import os
 
-from . import ir
+from . import ir, schedule
 
-EMITTER_VERSION = 5
+EMITTER_VERSION = 6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 KERNEL_HEADER = os.path.join(_HERE, 'csrc', 'colloc_kernel.cuh')
+
+# layout of ``opty_module_info`` (mirrored in csrc/runtime.cu)
+INFO_MAGIC = 0x4f505459   # 'OPTY'
+INFO_WORDS = 32
+MAX_MAPS = 8
+
+SCHEDULE_DEFAULTS = {
+    'schedule': True,       # False: plain emission order (output by output)
+    'reassociate': True,    # sums accumulate in arrival order
+    'live_budget': 40,      # float64 values the schedule may keep alive
+    'inline_cost': 2,       # values this cheap are never kept in a register
+    'remat_cost': 24,       # values this cheap may be recomputed after a gap
+    'fence_every': 0,       # > 0: a warp-level memory fence after this many
+                            # statements.  ptxas hoists global loads far
+                            # ahead of their use to overlap their latency;
+                            # on bodies of 10^4 statements that undoes the
+                            # schedule and spills.  The fence bounds how far
+                            # a load can move
+}
 
 
 def _lit(v):
@@ -52,21 +77,56 @@ def _lit(v):
     return s
 
 
+_CMP = {ir.LT: '<', ir.LE: '<=', ir.EQ: '==', ir.NE: '!=', ir.AND: '&&',
+        ir.OR: '||'}
+
+
+def _op_expr(T, i, r):
+    """C expression of tape operation ``i``; ``r(operand id)`` gives the text
+    of an operand.  Returns ``(type, expression)``."""
+    o = T.op[i]
+    a, b, c = T.a[i], T.b[i], T.c[i]
+    typ = 'double'
+    if o == ir.NEG:
+        e = '-{}'.format(r(a))
+    elif o == ir.ADD:
+        e = '{} + {}'.format(r(a), r(b))
+    elif o == ir.SUB:
+        e = '{} - {}'.format(r(a), r(b))
+    elif o == ir.MUL:
+        e = '{} * {}'.format(r(a), r(b))
+    elif o == ir.DIV:
+        e = '{} / {}'.format(r(a), r(b))
+    elif o in ir.UNARY_MATH:
+        e = '{}({})'.format(ir.OP_NAMES[o], r(a))
+    elif o in (ir.POW, ir.ATAN2, ir.MIN, ir.MAX):
+        e = '{}({}, {})'.format(ir.OP_NAMES[o], r(a), r(b))
+    elif o == ir.SIGN:
+        e = 'opty_sign({})'.format(r(a))
+    elif o == ir.SEL:
+        e = '({} ? {} : {})'.format(r(a), r(b), r(c))
+    elif o in ir.BOOL_OPS:
+        typ = 'bool'
+        if o == ir.NOT:
+            e = '!{}'.format(r(a))
+        else:
+            e = '({} {} {})'.format(r(a), _CMP[o], r(b))
+    else:
+        raise NotImplementedError(ir.OP_NAMES[o])
+    return typ, e
+
+
 class _BodyWriter(object):
     """Emits straight-line code for tape nodes on demand (depth-first from the
-    outputs, so temporaries are defined close to their first use).
+    outputs, so temporaries are defined close to their first use): the
+    single-thread invariants kernel (``mode='inv'``) and the pre-pass kernel
+    (``mode='pre'``, trajectory values from global memory)."""
 
-    ``mode``: ``'inv'`` single-thread invariants kernel, ``'pre'`` pre-pass
-    kernel (trajectory values from global memory), ``'main'`` group bodies
-    (trajectory values and derived rows from the staged shared-memory tile).
-    """
-
-    def __init__(self, prog, mode, derived_index=None):
+    def __init__(self, prog, mode):
         self.prog = prog
         self.T = prog.tape
         self.mode = mode
         self.varying_ctx = mode != 'inv'
-        self.derived_index = derived_index or {}
         self.done = set()
         self.lines = []
         self.num_ops = 0
@@ -79,14 +139,9 @@ class _BodyWriter(object):
         if self.varying_ctx:
             if o == ir.VIN:
                 slot = T.a[i]
-                if self.mode == 'pre':
-                    return '{}({})'.format('GB' if slot & 1 else 'GA',
-                                           slot >> 1)
-                return '{}({})'.format('XB' if slot & 1 else 'XA', slot >> 1)
+                return '{}({})'.format('GB' if slot & 1 else 'GA', slot >> 1)
             if not T.varying[i]:
                 return 'CI({})'.format(self.prog.inv_index[i])
-            if self.mode == 'main' and i in self.derived_index:
-                return 'XD({})'.format(self.derived_index[i])
             return 'v{}'.format(i)
         if o == ir.UIN:
             return 'uni[{}]'.format(T.a[i])
@@ -99,15 +154,11 @@ class _BodyWriter(object):
         varying = T.varying
         done = self.done
         vctx = self.varying_ctx
-        derived = self.derived_index if self.mode == 'main' else {}
 
         def is_leaf(i):
-            o = op_[i]
-            if o <= ir.UIN:
+            if op_[i] <= ir.UIN:
                 return True
             if vctx and not varying[i]:
-                return True
-            if i in derived:
                 return True
             return i in done
 
@@ -119,7 +170,10 @@ class _BodyWriter(object):
             if i in done:
                 continue
             if expanded:
-                self._emit(i)
+                typ, e = _op_expr(T, i, self.ref)
+                self.lines.append('const {} {} = {};'.format(
+                    typ, ('v{}' if vctx else 'w{}').format(i), e))
+                self.num_ops += 1
                 done.add(i)
                 continue
             stack.append((i, True))
@@ -128,162 +182,385 @@ class _BodyWriter(object):
                 if o >= 0 and not is_leaf(o):
                     stack.append((o, False))
 
-    def _emit(self, i):
-        T = self.T
-        o = T.op[i]
-        r = self.ref
-        a, b, c = T.a[i], T.b[i], T.c[i]
-        name = ('v{}' if self.varying_ctx else 'w{}').format(i)
-        typ = 'const double'
-        if o == ir.NEG:
-            e = '-{}'.format(r(a))
-        elif o == ir.ADD:
-            e = '{} + {}'.format(r(a), r(b))
-        elif o == ir.SUB:
-            e = '{} - {}'.format(r(a), r(b))
-        elif o == ir.MUL:
-            e = '{} * {}'.format(r(a), r(b))
-        elif o == ir.DIV:
-            e = '{} / {}'.format(r(a), r(b))
-        elif o in ir.UNARY_MATH:
-            e = '{}({})'.format(ir.OP_NAMES[o], r(a))
-        elif o in (ir.POW, ir.ATAN2, ir.MIN, ir.MAX):
-            e = '{}({}, {})'.format(ir.OP_NAMES[o], r(a), r(b))
-        elif o == ir.SIGN:
-            e = 'opty_sign({})'.format(r(a))
-        elif o == ir.SEL:
-            e = '({} ? {} : {})'.format(r(a), r(b), r(c))
-        elif o in ir.BOOL_OPS:
-            typ = 'const bool'
-            sym = {ir.LT: '<', ir.LE: '<=', ir.EQ: '==', ir.NE: '!=',
-                   ir.AND: '&&', ir.OR: '||'}
-            if o == ir.NOT:
-                e = '!{}'.format(r(a))
+
+# ---------------------------------------------------------------------------
+# phases: which columns of the node block are staged together
+# ---------------------------------------------------------------------------
+def _split_even_runs(col0, length, max_len, even):
+    """Cuts the column run ``[col0, col0+length)`` into pieces of at most
+    ``max_len`` columns.  With ``even`` every piece but possibly the last has
+    an even length whose half is odd where possible: the 16-byte
+    shared-memory stores of 8 consecutive lanes (row pitch 8*w bytes) then
+    fall into distinct bank groups."""
+    out = []
+    c = col0
+    end = col0 + length
+    while c < end:
+        w = min(max_len, end - c)
+        if even and w > 2 and w % 2 == 0 and (w // 2) % 2 == 0:
+            w -= 2
+        if even and w % 2 and end - c > w:
+            w -= 1
+        out.append((c, w))
+        c += w
+    return out
+
+
+def row_phases(col0, ncols, tile_cols, pair=None, even=True):
+    """Phases of the column run ``[col0, col0+ncols)`` (one equation row, or
+    two rows when ``P`` is odd): a list of phases, each a list of sub-tiles
+    ``(first column, width)`` whose widths add up to at most ``tile_cols``.
+
+    A row wider than ``tile_cols`` is cut so that the partial with respect to
+    state ``k`` at the current node (column ``k``) and at the adjacent node
+    (column ``pair + k``) land in the same phase: they share almost all of
+    their operations (both discretisations replace ``x`` and ``x'`` by linear
+    combinations of the two, opty/direct_collocation.py:2143-2156)."""
+    if ncols <= tile_cols:
+        return [_split_even_runs(col0, ncols, tile_cols, even)]
+    phases = []
+    if pair and 2 * pair <= ncols and not (even and pair % 2):
+        w = max(2, tile_cols // 2)
+        if even:
+            w -= w % 2
+            if w > 2 and (w // 2) % 2 == 0:
+                w -= 2
+        for k0 in range(0, pair, w):
+            k1 = min(pair, k0 + w)
+            phases.append([(col0 + k0, k1 - k0),
+                           (col0 + pair + k0, k1 - k0)])
+        tail0, tail = 2 * pair, ncols - 2 * pair
+        if tail:
+            used = sum(wd for _, wd in phases[-1])
+            if used + tail <= tile_cols:
+                phases[-1].extend(_split_even_runs(col0 + tail0, tail,
+                                                   tile_cols, even))
             else:
-                e = '({} {} {})'.format(r(a), sym[o], r(b))
-        else:
-            raise NotImplementedError(ir.OP_NAMES[o])
-        self.lines.append('{} {} = {};'.format(typ, name, e))
-        self.num_ops += 1
+                for piece in _split_even_runs(col0 + tail0, tail, tile_cols,
+                                              even):
+                    phases.append([piece])
+        return phases
+    return [[piece] for piece in _split_even_runs(col0, ncols, tile_cols,
+                                                  even)]
 
 
-def choose_tile_cols(requested):
-    """Tile width C (doubles) of the Jacobian staging tile.  C/2 must be odd
-    so that the 16-byte shared-memory stores of 8 consecutive lanes (row pitch
-    8*C bytes) fall into distinct bank groups."""
+def choose_tile_cols(requested, P, even=True):
+    """Columns of one staging buffer.  ``'auto'``: one whole equation row (two
+    when P is odd, so that a buffer starts at an even column) if that is at
+    most 64 columns, otherwise 52 (two paired runs of 26)."""
+    unit = P if (P % 2 == 0 or not even) else 2 * P
+    if requested == 'auto':
+        return unit if unit <= 64 else 52
     c = max(2, int(requested))
-    c -= c % 2
-    if (c // 2) % 2 == 0:
-        c -= 2
+    if even:
+        c -= c % 2
     return max(2, c)
 
 
-def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
+# ---------------------------------------------------------------------------
+# group bodies
+# ---------------------------------------------------------------------------
+class _GroupLayout(object):
+    """Output slots, phases and sub-tiles of one output group."""
+
+    def __init__(self, prog, gc0, gc1, tile_cols, pair, tma_store, tile_bufs,
+                 map_index):
+        P = prog.P
+        T = prog.tape
+        even = bool(tma_store)
+        unit = P if (P % 2 == 0 or not even) else 2 * P
+        self.slots = []        # (kind, ...) parallel to ``roots``
+        self.roots = []
+        self.phases = []       # per phase: dict(buf, subtiles, slots)
+        assert gc0 % P == 0 and gc1 % P == 0
+        c = gc0
+        while c < gc1:
+            ncols = min(unit, gc1 - c)
+            rp = row_phases(c, ncols, tile_cols,
+                            pair if ncols == P else None, even)
+            for pi, subtiles in enumerate(rp):
+                t = len(self.phases)
+                ph = {'buf': t % tile_bufs, 'subtiles': [], 'slots': []}
+                off = 0
+                for (s0, w) in subtiles:
+                    mi = map_index(w) if tma_store else 0
+                    ph['subtiles'].append((mi, off, w, s0))
+                    col = s0
+                    while col < s0 + w:
+                        pairable = (w % 2 == 0 and (col - s0) % 2 == 0 and
+                                    col + 1 < s0 + w)
+                        j0, k0 = divmod(col, P)
+                        if pairable:
+                            j1, k1 = divmod(col + 1, P)
+                            self.slots.append(('js2', t, ph['buf'], off, w,
+                                               col - s0))
+                            self.roots.append((prog.jac[j0][k0],
+                                               prog.jac[j1][k1]))
+                            col += 2
+                        else:
+                            self.slots.append(('js1', t, ph['buf'], off, w,
+                                               col - s0))
+                            self.roots.append((prog.jac[j0][k0],))
+                            col += 1
+                        ph['slots'].append(len(self.slots) - 1)
+                    off += 32 * w
+                self.phases.append(ph)
+                # the residual of a row is due with the row's last phase
+                if pi == len(rp) - 1 and prog.con:
+                    for j in range(c // P, (c + ncols) // P):
+                        self.slots.append(('con', t, j))
+                        self.roots.append((prog.con[j],))
+                        ph['slots'].append(len(self.slots) - 1)
+            c += ncols
+        self.stored = sum(w for ph in self.phases
+                          for (_, _, w, _) in ph['subtiles'])
+        del T
+
+
+class _ScheduledWriter(object):
+    """Turns the events of a :class:`schedule.Schedule` into CUDA-C lines."""
+
+    def __init__(self, prog, derived_index, sched):
+        self.prog = prog
+        self.T = prog.tape
+        self.derived_index = derived_index
+        self.sched = sched
+        self.dag = sched.dag
+
+    def leaf(self, i):
+        T = self.T
+        o = T.op[i]
+        if o == ir.CONST:
+            return _lit(T.val[i])
+        if o == ir.VIN:
+            slot = T.a[i]
+            return '{}({})'.format('XB' if slot & 1 else 'XA', slot >> 1)
+        if i in self.derived_index:
+            return 'XD({})'.format(self.derived_index[i])
+        if not T.varying[i]:
+            return 'CI({})'.format(self.prog.inv_index[i])
+        raise AssertionError('not a leaf: {}'.format(i))
+
+    def expr(self, consumer, i):
+        """Text of value ``i`` as read inside ``consumer``."""
+        dag = self.dag
+        kind = dag.kind_of(i)
+        if kind == 0:
+            return self.leaf(i)
+        if i in dag.regset and (consumer, i) not in dag.inline_edges:
+            return 'v{}'.format(i)
+        if kind == 1:
+            return self.leaf(i)
+        if i in dag.terms:
+            return '(' + self.sum_text(consumer, dag.terms[i]) + ')'
+        _, e = _op_expr(self.T, i, lambda o: self.expr(consumer, o))
+        return '(' + e + ')'
+
+    def sum_text(self, consumer, terms):
+        out = []
+        for sg, t in terms:
+            e = self.expr(consumer, t)
+            if not out:
+                out.append(e if sg > 0 else '-' + e)
+            else:
+                out.append((' + ' if sg > 0 else ' - ') + e)
+        return ''.join(out)
+
+    def lines_for(self, layout, fence_every=0):
+        dag = self.dag
+        T = self.T
+        lines = []
+        slots = layout.slots
+        phases = layout.phases
+        left = [sum(1 for k in ph['slots'] if slots[k][0] != 'con')
+                for ph in phases]
+        begun = [False] * len(phases)
+        num_ops = 0
+        since_fence = 0
+        for e in self.sched.events:
+            kind = e[0]
+            if fence_every and kind != schedule.OUT:
+                since_fence += 1
+                if since_fence >= fence_every:
+                    lines.append('OPTY_FENCE();')
+                    since_fence = 0
+            if kind == schedule.LOAD:
+                v = e[1]
+                lines.append('const double v{} = {};'.format(v, self.leaf(v)))
+            elif kind == schedule.OP:
+                v = e[1]
+                if v in dag.terms:
+                    lines.append('const double v{} = {};'.format(
+                        v, self.sum_text(v, dag.terms[v])))
+                else:
+                    typ, ex = _op_expr(T, v, lambda o, v=v: self.expr(v, o))
+                    lines.append('const {} v{} = {};'.format(typ, v, ex))
+                num_ops += 1
+            elif kind == schedule.ACC:
+                s, j, first = e[1], e[2], e[3]
+                terms = dag.terms[s]
+                if first:
+                    # terms that read no register value are folded in here
+                    start = [terms[j]] + [
+                        t for k, t in enumerate(terms)
+                        if k != j and not dag.term_rops[s][k]]
+                    lines.append('double v{} = {};'.format(
+                        s, self.sum_text(s, start)))
+                else:
+                    sg, t = terms[j]
+                    lines.append('v{} {}= {};'.format(
+                        s, '+' if sg > 0 else '-', self.expr(s, t)))
+                num_ops += 1
+            else:
+                k = e[1]
+                slot = slots[k]
+                consumer = (schedule.OUT, k)
+                vals = [self.expr(consumer, r) for r in dag.outputs[k]]
+                if slot[0] == 'con':
+                    lines.append('OPTY_CON({}, {});'.format(slot[2], vals[0]))
+                    continue
+                t = slot[1]
+                if not begun[t]:
+                    begun[t] = True
+                    lines.append('OPTY_PHASE_BEGIN({});'.format(t))
+                if slot[0] == 'js2':
+                    lines.append('OPTY_JS2({}, {}, {}, {}, {}, {});'.format(
+                        slot[2], slot[3], slot[4], slot[5], vals[0], vals[1]))
+                else:
+                    lines.append('OPTY_JS1({}, {}, {}, {}, {});'.format(
+                        slot[2], slot[3], slot[4], slot[5], vals[0]))
+                left[t] -= 1
+                if left[t] == 0:
+                    lines.append('OPTY_FLUSH_BEGIN()')
+                    for (mi, off, w, col0) in phases[t]['subtiles']:
+                        lines.append('OPTY_TSTORE({}, {}, {}, {}, {})'.format(
+                            mi, phases[t]['buf'], off, w, col0))
+                    lines.append('OPTY_FLUSH_END()')
+        assert all(v == 0 for v in left)
+        lines.append('OPTY_DRAIN();')
+        return lines, num_ops
+
+
+# shared state of the worker processes that emit group bodies in parallel
+# (set before the pool forks; the tape is far too large to pickle per task)
+_WORK = {}
+
+
+def _emit_group(g):
+    prog = _WORK['prog']
+    opts = _WORK['opts']
+    gc0, gc1 = _WORK['groups'][g]
+    widths = _WORK['widths']
+
+    def map_index(w):
+        return widths.index(w)
+    layout = _GroupLayout(prog, gc0, gc1, _WORK['tile_cols'], _WORK['pair'],
+                          _WORK['tma_store'], _WORK['tile_bufs'], map_index)
+    stop = _WORK['stop']
+    phase_lists = [ph['slots'] for ph in layout.phases]
+    if opts['schedule']:
+        sched = schedule.schedule_body(
+            prog.tape, layout.roots, stop, phases=phase_lists,
+            reassociate=opts['reassociate'], inline_cost=opts['inline_cost'],
+            remat_cost=opts['remat_cost'], live_budget=opts['live_budget'])
+    else:
+        # plain order: slots in layout order (phases are contiguous there)
+        sched = schedule.plain_order(prog.tape, layout.roots, stop)
+    writer = _ScheduledWriter(prog, _WORK['derived_index'], sched)
+    lines, num_ops = writer.lines_for(layout, int(opts['fence_every']))
+    meta = {'rows': [gc0 // prog.P, gc1 // prog.P], 'cols': [gc0, gc1],
+            'col0': gc0, 'ncols': layout.stored, 'ops': sched.num_ops,
+            'statements': num_ops, 'peak_live': sched.peak_live,
+            'phases': len(layout.phases)}
+    return lines, meta
+
+
+def group_widths(prog, groups, tile_cols, pair, tma_store):
+    """Distinct sub-tile widths of all groups (one output tensor map each)."""
+    widths = []
+    P = prog.P
+    even = bool(tma_store)
+    unit = P if (P % 2 == 0 or not even) else 2 * P
+    for gc0, gc1 in groups:
+        c = gc0
+        while c < gc1:
+            ncols = min(unit, gc1 - c)
+            for subtiles in row_phases(c, ncols, tile_cols,
+                                       pair if ncols == P else None, even):
+                for _, w in subtiles:
+                    if w not in widths:
+                        widths.append(w)
+            c += ncols
+    return sorted(widths)
+
+
+def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
                 min_blocks_per_sm=4, tma_load=True, tma_store=True,
-                derived=(), debug_nostore=False, tile_bufs=2, debug_reps=1,
-                const_runs=(), only_groups=None, with_aux=True,
-                persistent=False, tile_major=False,
-                persistent_block_stores=True):
+                derived=(), debug_nostore=False, tile_bufs=2,
+                only_groups=None, with_aux=True, pair=None,
+                schedule_options=None, workers=1):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
-    (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block;
-    a group also owns the residuals of the rows that start inside it).  ``derived`` lists the tape ids
-    that the pre-pass kernel evaluates once per node into derived rows.
-    ``const_runs`` lists ``(col0, length)`` column runs of the node block
-    whose entries are the same for every node: the group bodies skip them
-    and the runtime's replicator kernel copies one shared-memory image of
-    them into every node row with TMA tile stores.
+    (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block,
+    whole equations each; a group also owns the residuals of its rows).
+    ``derived`` lists the tape ids that the pre-pass kernel evaluates once
+    per node into derived rows.  ``pair``: number of states ``n`` when the
+    columns ``k`` and ``n + k`` of a row are the partials with respect to the
+    same state at the two nodes of the stencil (collocation programs), else
+    None.
 
     Large problems are compiled as several modules in parallel: with
     ``only_groups = (g0, g1)`` the module contains the bodies and the main
-    kernel of groups ``g0 .. g1-1`` only (group and store-segment indices
-    inside it are local); ``with_aux=False`` leaves out the invariants and
-    pre-pass kernels (the first module carries them).
-
-    ``persistent=True`` emits the persistent variant of the main kernel
-    (``csrc/colloc_persistent.cuh``): one block per SM bound to one group,
-    warps looping over node tiles along a host-made schedule, the pre-pass
-    as phase 0 of the same launch."""
+    kernel of groups ``g0 .. g1-1`` only; ``with_aux=False`` leaves out the
+    invariants and pre-pass kernels (the first module carries them)."""
     T = prog.tape
     M, P, K, R = prog.M, prog.P, prog.K, prog.R
-    C = choose_tile_cols(tile_cols)
-    if warps_per_block > 4 and warps_per_block % 4 and not persistent:
+    tma_store = bool(tma_store) and K % 2 == 0
+    C = choose_tile_cols(tile_cols, P, even=tma_store)
+    if warps_per_block > 4 and warps_per_block % 4:
         raise ValueError('warps_per_block above 4 must be a multiple of 4')
+    tile_bufs = int(tile_bufs)
+    if tile_bufs not in (1, 2):
+        raise ValueError('tile_bufs must be 1 or 2')
+    opts = dict(SCHEDULE_DEFAULTS)
+    opts.update(schedule_options or {})
     ninv = len(prog.inv_nodes)
     derived = list(derived)
     derived_index = {nid: k for k, nid in enumerate(derived)}
     D = len(derived)
-
-    const_runs = sorted(const_runs)
-    carved = [False] * K
-    for a, ln in const_runs:
-        assert a % 2 == 0 and ln % 2 == 0 and tma_store
-        for c in range(a, a + ln):
-            carved[c] = True
-    # store segments: maximal runs of non-carved columns inside one group;
-    # each gets its own TMA descriptor (box C x 32, clipped at the segment end)
-    segments = []          # (col0, ncols)
-    group_segments = []    # per group: list of segment ids
-    for (gc0, gc1) in groups:
-        ids = []
-        c = gc0
-        end = gc1
-        while c < end:
-            if carved[c]:
-                c += 1
-                continue
-            e = c
-            while e < end and not carved[e]:
-                e += 1
-            ids.append(len(segments))
-            segments.append((c, e - c))
-            c = e
-        group_segments.append(ids)
-    seg_of_col = {}
-    for sid, (a, ln) in enumerate(segments):
-        for c in range(a, a + ln):
-            seg_of_col[c] = sid
-    ncc = sum(ln for _, ln in const_runs)
+    groups = [tuple(g) for g in groups]
     g0, g1 = only_groups if only_groups is not None else (0, len(groups))
-    seg_first = group_segments[g0][0] if group_segments[g0] else 0
-    local_segs = [sid for g in range(g0, g1) for sid in group_segments[g]]
-    assert local_segs == list(range(seg_first, seg_first + len(local_segs)))
+    widths = group_widths(prog, groups, C, pair, tma_store)
+    if tma_store and len(widths) > MAX_MAPS:
+        raise ValueError('The module needs {} distinct staging tile widths, '
+                         'at most {} are supported.'.format(
+                             len(widths), MAX_MAPS))
+    if not tma_store:
+        map_widths = [2]        # unused descriptor slot
+    else:
+        map_widths = widths
 
     out = []
     w = out.append
     w('// generated by opty_b200.codegen (emitter v{}); do not edit'.format(
         EMITTER_VERSION))
-    w('#define OPTY_NSEGS {}'.format(max(len(local_segs), 1)))
+    w('#define OPTY_NMAPS {}'.format(len(map_widths)))
     w('#define OPTY_M {}'.format(M))
     w('#define OPTY_P {}'.format(P))
     w('#define OPTY_K {}'.format(K))
     w('#define OPTY_R {}'.format(R))
     w('#define OPTY_D {}'.format(D))
-    w('#define OPTY_C {}'.format(C))
+    w('#define OPTY_TILE_DOUBLES {}'.format(32 * C))
     w('#define OPTY_NGROUPS {}'.format(g1 - g0))
     w('#define OPTY_NINV {}'.format(max(ninv, 1)))
     w('#define OPTY_NUNI {}'.format(max(prog.num_uniform, 1)))
-    if persistent:
-        # the base skeleton is used with its per-warp geometry
-        w('#define OPTY_WARPS 1')
-        w('#define OPTY_PWARPS {}'.format(warps_per_block))
-        if not persistent_block_stores:
-            w('#define OPTY_PERSIST_BLOCK_STORES 0')
-        w('#define OPTY_MIN_BLOCKS 1')
-    else:
-        w('#define OPTY_WARPS {}'.format(warps_per_block))
-        w('#define OPTY_MIN_BLOCKS {}'.format(min_blocks_per_sm))
+    w('#define OPTY_WARPS {}'.format(warps_per_block))
+    w('#define OPTY_MIN_BLOCKS {}'.format(min_blocks_per_sm))
     w('#define OPTY_TMA_LOAD {}'.format(int(tma_load)))
     w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
-    w('#define OPTY_NBUF {}'.format(int(tile_bufs)))
-    if tile_major:
-        w('#define OPTY_TILE_MAJOR 1')
+    w('#define OPTY_NBUF {}'.format(tile_bufs))
     if debug_nostore:
         w('#define OPTY_DEBUG_NOSTORE {}'.format(int(debug_nostore)))
-    if debug_reps != 1:
-        w('#define OPTY_DEBUG_REPS {}'.format(int(debug_reps)))
     w('#include "colloc_kernel.cuh"')
-    if persistent:
-        w('#include "colloc_persistent.cuh"')
     w('')
 
     # ---- invariants kernel -------------------------------------------
@@ -314,137 +591,53 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     for ks in by_arg.values():
         pre_chunks.append(ks)
     pre_groups = len(pre_chunks)
-    # pattern of the constant runs (replicated into every node row by the
-    # runtime's opty_replicate_kernel): literal value, or index into the
-    # node-invariant table, in run order
-    const_lit, const_inv = [], []
-    for a, ln in const_runs:
-        for c in range(a, a + ln):
-            e = prog.jac[c // P][c % P]
-            if T.op[e] == ir.CONST:
-                const_lit.append(float(T.val[e]))
-                const_inv.append(-1)
-            else:
-                assert not T.varying[e]
-                const_lit.append(0.0)
-                const_inv.append(prog.inv_index[e])
     pre_ops = 0
     if with_aux:
-        pre_cases = []
+        w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
+        w('opty_colloc_pre(const OptyParams p)')
+        w('{')
+        w('  OPTY_PRE_BEGIN();')
+        w('  switch (opty_pg) {')
         for pg, ks in enumerate(pre_chunks):
             bw = _BodyWriter(prog, 'pre')
             for k in ks:
                 bw.need(derived[k])
                 bw.lines.append('OPTY_DRV({}, {});'.format(
                     k, bw.ref(derived[k])))
-            pre_cases.append('    case {}: {{'.format(pg))
-            pre_cases.extend('      ' + line for line in bw.lines)
-            pre_cases.append('    } break;')
+            w('    case {}: {{'.format(pg))
+            for line in bw.lines:
+                w('      ' + line)
+            w('    } break;')
             pre_ops += bw.num_ops
-        if persistent:
-            # phase 0 of the persistent kernel calls the same bodies
-            w('static __device__ void opty_pre_unit(const OptyParams& p, '
-              'const int node, const int opty_pg)')
-            w('{')
-            w('  const double* xg = p.traj + node;')
-            w('  double* drv = p.traj + (long long)OPTY_R * p.ldt + node;')
-            w('  switch (opty_pg) {')
-            for line in pre_cases:
-                w(line)
-            w('    default: break;')
-            w('  }')
-            w('}')
-            w('')
-        w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
-        w('opty_colloc_pre(const OptyParams p)')
-        w('{')
-        w('  OPTY_PRE_BEGIN();')
-        if persistent:
-            w('  opty_pre_unit(p, node, opty_pg);')
-            w('  (void)xg; (void)drv;')
-        else:
-            w('  switch (opty_pg) {')
-            for line in pre_cases:
-                w(line)
-            w('    default: break;')
-            w('  }')
+        w('    default: break;')
+        w('  }')
         w('}')
         w('')
 
-    # ---- group bodies --------------------------------------------------
+    # ---- group bodies (scheduled, possibly in parallel) ------------------
+    _WORK.update(prog=prog, opts=opts, groups=groups, widths=map_widths,
+                 tile_cols=C, pair=pair, tma_store=tma_store,
+                 tile_bufs=tile_bufs, stop=frozenset(derived),
+                 derived_index=derived_index)
+    todo = list(range(g0, g1))
+    workers = max(1, min(int(workers), len(todo)))
+    if workers > 1:
+        import multiprocessing
+        with multiprocessing.get_context('fork').Pool(workers) as pool:
+            results = pool.map(_emit_group, todo, chunksize=1)
+    else:
+        results = [_emit_group(g) for g in todo]
+    _WORK.clear()
     group_meta = []
-    for g, (gc0, gc1) in enumerate(groups):
-        if not g0 <= g < g1:
-            continue
-        bw = _BodyWriter(prog, 'main', derived_index)
-        body = bw.lines
+    for g, (lines, gm) in zip(todo, results):
         w('static __device__ __forceinline__ void opty_group_{}('
           'const OptyCtx& ctx)'.format(g))
         w('{')
-        state = {'seg': None, 'cc': 0, 'chunk': 0, 'pending': None,
-                 'stored': 0}
-
-        def flush():
-            sid = state['seg']
-            cc = state['cc']
-            ncols_in_chunk = cc % C or C
-            q = (cc - 1) // C
-            body.append('OPTY_FLUSH({}, {}, {}, {}, {});'.format(
-                sid - seg_first, q, state['chunk'] % tile_bufs,
-                segments[sid][0], ncols_in_chunk))
-            state['chunk'] += 1
-
-        def close_segment():
-            assert state['pending'] is None
-            if state['seg'] is not None and state['cc'] % C != 0:
-                flush()
-            state['seg'] = None
-            state['cc'] = 0
-
-        for col in range(gc0, gc1):
-            j, k = divmod(col, P)
-            if k == 0 and prog.con:
-                bw.need(prog.con[j])
-                body.append('OPTY_CON({}, {});'.format(
-                    j, bw.ref(prog.con[j])))
-            if carved[col]:
-                continue
-            sid = seg_of_col[col]
-            if sid != state['seg']:
-                close_segment()
-                state['seg'] = sid
-            seg_ncols = segments[sid][1]
-            e = prog.jac[j][k]
-            bw.need(e)
-            cc = state['cc']
-            tc = cc % C
-            buf = state['chunk'] % tile_bufs
-            pending = state['pending']
-            if pending is None and tc % 2 == 0 and tc + 1 < C and \
-                    cc + 1 < seg_ncols:
-                state['pending'] = (tc, bw.ref(e))
-            elif pending is not None:
-                body.append('OPTY_JS2({}, {}, {}, {});'.format(
-                    buf, pending[0], pending[1], bw.ref(e)))
-                state['pending'] = None
-            else:
-                body.append('OPTY_JS1({}, {}, {});'.format(
-                    buf, tc, bw.ref(e)))
-            state['cc'] = cc + 1
-            state['stored'] += 1
-            if state['cc'] % C == 0 and state['pending'] is None:
-                flush()
-        close_segment()
-        body.append('OPTY_DRAIN();')
-        for line in body:
+        for line in lines:
             w('  ' + line)
         w('}')
         w('')
-        group_meta.append({'rows': [gc0 // P, -(-gc1 // P)],
-                           'cols': [gc0, gc1], 'col0': gc0,
-                           'ncols': state['stored'],
-                           'segments': group_segments[g],
-                           'ops': bw.num_ops, 'chunks': state['chunk']})
+        group_meta.append(gm)
 
     # blockIdx.y -> group: most expensive groups are launched first
     order = sorted(range(len(group_meta)),
@@ -453,44 +646,42 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
     w('__device__ const int opty_group_order[OPTY_NGROUPS] = {{{}}};'.format(
         ', '.join(str(g) for g in order)))
     w('')
-    if persistent:
-        w('extern "C" __global__ void __launch_bounds__(OPTY_PTHREADS, 1)')
-        w('opty_colloc_eval(const __grid_constant__ OptyTmaps tm, '
-          'const OptyParams p, const OptyPersist ps)')
-        w('{')
-        w('  OPTY_PERSIST_BEGIN()')
-        w('  OPTY_PERSIST_LOOP_BEGIN()')
-        w('  switch (opty_g) {')
-        for g in range(g0, g1):
-            w('    case {}: opty_group_{}(ctx); break;'.format(g - g0, g))
-        w('    default: break;')
-        w('  }')
-        w('  OPTY_PERSIST_LOOP_END()')
-        w('  OPTY_PERSIST_END()')
-        w('}')
-        w('')
-    else:
-        w('extern "C" __global__ void __launch_bounds__(OPTY_THREADS, '
-          'OPTY_MIN_BLOCKS)')
-        w('opty_colloc_eval(const __grid_constant__ OptyTmaps tm, '
-          'const OptyParams p)')
-        w('{')
-        w('  OPTY_KERNEL_BEGIN()')
-        if debug_reps != 1:
-            # measurement aid: the same tile is evaluated several times,
-            # passes after the first find the group body in the instruction
-            # caches
-            w('#pragma unroll 1')
-            w('  for (int opty_rep = 0; opty_rep < OPTY_DEBUG_REPS; '
-              '++opty_rep)')
-        w('  switch (opty_g) {')
-        for g in range(g0, g1):
-            w('    case {}: opty_group_{}(ctx); break;'.format(g - g0, g))
-        w('    default: break;')
-        w('  }')
-        w('  OPTY_KERNEL_END()')
-        w('}')
-        w('')
+    info = [0] * INFO_WORDS
+    info[0] = INFO_MAGIC
+    info[1] = EMITTER_VERSION
+    info[2] = warps_per_block
+    info[3] = g1 - g0
+    info[4] = D
+    info[5] = pre_groups
+    info[6] = int(tma_load)
+    info[7] = 1 if tma_store else 0
+    info[8] = tile_bufs
+    info[9] = 32 * C
+    info[10] = len(map_widths)
+    for k, mw in enumerate(map_widths):
+        info[11 + k] = mw
+    info[19] = ninv
+    info[20] = R
+    info[21] = M
+    info[22] = P
+    info[23] = 1 if with_aux else 0
+    w('extern "C" __device__ const int opty_module_info[{}] = {{{}}};'.format(
+        INFO_WORDS, ', '.join(str(v) for v in info)))
+    w('')
+    w('extern "C" __global__ void __launch_bounds__(OPTY_THREADS, '
+      'OPTY_MIN_BLOCKS)')
+    w('opty_colloc_eval(const __grid_constant__ OptyTmaps tm, '
+      'const OptyParams p)')
+    w('{')
+    w('  OPTY_KERNEL_BEGIN()')
+    w('  switch (opty_g) {')
+    for g in range(g0, g1):
+        w('    case {}: opty_group_{}(ctx); break;'.format(g - g0, g))
+    w('    default: break;')
+    w('  }')
+    w('  OPTY_KERNEL_END()')
+    w('}')
+    w('')
 
     meta = {
         'emitter_version': EMITTER_VERSION,
@@ -498,12 +689,7 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         'num_groups': g1 - g0,
         'groups': group_meta,
         'group_range': [g0, g1],
-        'segment_range': [seg_first, seg_first + len(local_segs)],
-        'segments': [list(sg) for sg in segments],
-        'const_runs': [list(cr) for cr in const_runs],
-        'const_image_doubles': ncc,
-        'const_lit': const_lit,
-        'const_inv': const_inv,
+        'map_widths': list(map_widths),
         'num_inv': ninv,
         'num_uniform': prog.num_uniform,
         'inv_ops': inv_ops,
@@ -514,10 +700,9 @@ def emit_module(prog, groups, method, tile_cols=30, warps_per_block=2,
         'min_blocks_per_sm': min_blocks_per_sm,
         'tma_load': int(tma_load),
         'tma_store': bool(tma_store),
-        'tile_bufs': int(tile_bufs),
-        'persistent': bool(persistent),
-        'persistent_block_stores': bool(persistent_block_stores),
+        'tile_bufs': tile_bufs,
         'method': method,
+        'schedule': opts,
         'entry_kind': prog.entry_kind(),
         'stats': prog.stats(),
     }

@@ -1,17 +1,17 @@
 // Hand-written sm_100a skeleton of the collocation constraint + Jacobian kernels.
 //
 // The generated module (opty_b200/codegen.py) defines the problem sizes
-// (OPTY_M, OPTY_P, OPTY_K, OPTY_R, OPTY_D, OPTY_C, ...), the straight-line body
-// of the pre-pass kernel and one straight-line `opty_group_<g>` device function
-// per output group, then includes this file, which supplies everything around
-// the arithmetic:
+// (OPTY_M, OPTY_P, OPTY_K, OPTY_R, OPTY_D, ...), the straight-line body of the
+// pre-pass kernel and one straight-line `opty_group_<g>` device function per
+// output group, then includes this file, which supplies everything around the
+// arithmetic:
 //
 //   * the block -> (node tile, output group) mapping,
 //   * staging of a tile's slice of the trajectory matrix (plus the derived rows
 //     written by the pre-pass) into shared memory with 2-D TMA tile loads
 //     (cp.async.bulk.tensor, mbarrier completion),
-//   * the per-warp, double-buffered, bank-conflict-free staging tile for the
-//     node-major Jacobian block and its drain by 2-D TMA tile stores,
+//   * the per-warp shared-memory staging buffers for the node-major Jacobian
+//     block and their drain by 2-D TMA tile stores,
 //   * a coalesced warp-per-node fallback for shapes TMA cannot describe.
 //
 // Work mapping: lane = collocation node (all lanes of a warp execute the same
@@ -19,6 +19,14 @@
 // group.  It replaces the node loop of the reference's generated Cython
 // (`for i in prange(n)`, opty/utils.py:524-526) and the per-node `eval_matrix`
 // C function (opty/utils.py:483-494).
+//
+// A group body is a sequence of PHASES.  A phase owns a few column runs of the
+// node block ("sub-tiles": [32 nodes][w columns], dense, one after the other in
+// one of the warp's OPTY_NBUF staging buffers); the body writes the phase's
+// entries in whatever order the register-pressure scheduler (schedule.py)
+// produced them, then hands every sub-tile to the TMA unit with one tile store.
+// Sub-tiles of the same width share a tensor map over the whole Jacobian
+// ({K, nodes}, box {w, 32}); rows beyond the shard are clipped by the TMA unit.
 //
 // Data layout (all float64):
 //   traj : [R + D][ldt]  rows = states, unknown inputs, known inputs, then the D
@@ -50,18 +58,16 @@
 #define OPTY_XBOX (OPTY_XSEG + 2)
 #define OPTY_NSEG (OPTY_THREADS / OPTY_XSEG)
 #define OPTY_XSEG_BYTES (((OPTY_RD * OPTY_XBOX * 8) + 127) / 128 * 128)
-#define OPTY_TILE_DOUBLES (32 * OPTY_C)
 #ifndef OPTY_NBUF
-#define OPTY_NBUF 2  // staging tiles per warp (TMA stores in flight + 1)
+#define OPTY_NBUF 2  // staging buffers per warp (phases whose TMA stores may be in flight + 1)
 #endif
 #ifndef OPTY_DEBUG_NOSTORE
-#define OPTY_DEBUG_NOSTORE 0  // measurement aid: skip the Jacobian tile stores
+#define OPTY_DEBUG_NOSTORE 0  // measurement aid: 1 = skip the Jacobian tile stores (wrong results)
 #endif
 
 struct OptyTmaps {
-  CUtensorMap in;                 // traj as {cols, R + D}
-  CUtensorMap out[OPTY_NSEGS];    // store segment s (a run of columns written by one group) of jac as
-                                  // {ncols_s, nodes}
+  CUtensorMap in;               // traj as {cols, R + D}, box {OPTY_XBOX, R + D}
+  CUtensorMap out[OPTY_NMAPS];  // jac as {K, nodes}, box {OPTY_MAP_WIDTH[i], 32}
 };
 
 // node-invariant sub-expressions, filled by the host from opty_colloc_inv
@@ -69,12 +75,14 @@ __constant__ double opty_ci[OPTY_NINV];
 #define CI(k) opty_ci[k]
 
 struct OptyCtx {
-  const double* xs;  // this lane's column in its staged segment (row pitch OPTY_XBOX) or, with direct
-                     // input loads, in the trajectory matrix itself (row pitch ldt)
+#if OPTY_TMA_LOAD == 2
+  const double* xg;  // this lane's column of the trajectory matrix (row pitch ldt)
+#else
+  uint32_t xs;       // shared-memory address of this lane's column in its staged segment (row pitch OPTY_XBOX)
+#endif
   long long ldt;
   double* con;       // &con[node of this lane]
-  double* trow0;     // this lane's row in tile buffer 0 (buffer b: + b*OPTY_TILE_DOUBLES)
-  double* tile0;     // warp's tile buffer 0
+  double* tile0;     // the warp's staging buffer 0 (buffer b: + b * OPTY_TILE_DOUBLES)
   double* jac;       // p.jac
   const OptyTmaps* tm;
   long long ldc;
@@ -128,86 +136,99 @@ static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map,
                    reinterpret_cast<uint64_t>(map)),
                "r"(c0), "r"(c1), "r"(opty_smem_u32(src))
                : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------
 // main kernel: operand and output macros used by the generated group bodies
 // ---------------------------------------------------------------------------
-// trajectory value of row r at this lane's node (A) and at the next node (B);
-// derived row d (pre-pass output) at this lane's node
+// Input loads are `asm volatile`: every textual load is one load instruction.
+// The scheduler decides where an input is held in a register and where it is
+// read again (schedule.py); a compiler that merged the loads would pin the
+// register for the whole distance between them.
 #if OPTY_TMA_LOAD == 2
 // direct mode: no staging; lanes read consecutive columns of a row (coalesced,
 // read-only path), the neighbour column comes from the same cache lines
-#define XA(r) __ldg(ctx.xs + (long long)(r) * ctx.ldt)
-#define XB(r) __ldg(ctx.xs + (long long)(r) * ctx.ldt + 1)
-#define XD(d) __ldg(ctx.xs + (long long)(OPTY_R + (d)) * ctx.ldt)
+static __device__ __forceinline__ double opty_ldin(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+#define XA(r) opty_ldin(ctx.xg + (long long)(r) * ctx.ldt)
+#define XB(r) opty_ldin(ctx.xg + (long long)(r) * ctx.ldt + 1)
+#define XD(d) opty_ldin(ctx.xg + (long long)(OPTY_R + (d)) * ctx.ldt)
 #else
-#define XA(r) ctx.xs[(r) * OPTY_XBOX]
-#define XB(r) ctx.xs[(r) * OPTY_XBOX + 1]
-#define XD(d) ctx.xs[(OPTY_R + (d)) * OPTY_XBOX]
+static __device__ __forceinline__ double opty_ldin(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+#define XA(r) opty_ldin(ctx.xs + (r) * (OPTY_XBOX * 8))
+#define XB(r) opty_ldin(ctx.xs + (r) * (OPTY_XBOX * 8) + 8)
+#define XD(d) opty_ldin(ctx.xs + (OPTY_R + (d)) * (OPTY_XBOX * 8))
 #endif
+
+// scheduling fence: no memory operation moves across it (see codegen.py, `fence_every`)
+#define OPTY_FENCE() __syncwarp()
 
 #define OPTY_CON(j, val)                                       \
   do {                                                         \
     if (ctx.active) ctx.con[(long long)(j) * ctx.ldc] = (val); \
   } while (0)
 
-#define OPTY_TROW(buf) (ctx.trow0 + (buf) * OPTY_TILE_DOUBLES)
-#define OPTY_JS2(buf, tc, v0, v1) *reinterpret_cast<double2*>(OPTY_TROW(buf) + (tc)) = make_double2((v0), (v1))
-#define OPTY_JS1(buf, tc, v0) OPTY_TROW(buf)[(tc)] = (v0)
+// this lane's row of the sub-tile that starts `off` doubles into staging buffer `buf` and is `w` columns wide
+#define OPTY_TROW(buf, off, w) (ctx.tile0 + (buf) * OPTY_TILE_DOUBLES + (off) + ctx.lane * (w))
+#define OPTY_JS2(buf, off, w, c, v0, v1) \
+  *reinterpret_cast<double2*>(OPTY_TROW(buf, off, w) + (c)) = make_double2((v0), (v1))
+#define OPTY_JS1(buf, off, w, c, v0) OPTY_TROW(buf, off, w)[(c)] = (v0)
 
-// Hands the warp's finished tile (chunk `Q` of store segment `SEG`: node rows
-// ctx.node..+31, Jacobian columns SEGCOL0 + Q*C .. + NCOLS, staged in tile
-// buffer `BUF`) to the TMA unit, or copies it out with coalesced
-// warp-per-node stores.
-template <int SEG, int Q, int BUF, int SEGCOL0, int NCOLS>
-static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
-  double* tile = ctx.tile0 + BUF * OPTY_TILE_DOUBLES;
+// first statement of phase `t` (static index inside the body): its staging
+// buffer is free again once at most OPTY_NBUF-1 younger store groups may still
+// be reading theirs
 #if OPTY_TMA_STORE
-  // make the generic-proxy st.shared visible to the async proxy, then one
-  // lane issues the tile store; at most OPTY_NBUF-1 older stores may still be
-  // reading their buffers when the warp continues with the next buffer
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#define OPTY_PHASE_BEGIN(t)                                                                                   \
+  do {                                                                                                        \
+    if ((t) >= OPTY_NBUF) {                                                                                   \
+      if (ctx.lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(OPTY_NBUF - 1) : "memory"); \
+      __syncwarp();                                                                                           \
+    }                                                                                                         \
+  } while (0)
+// the phase's entries are in shared memory: make the generic-proxy stores
+// visible to the async proxy, then one lane issues the tile stores
+#define OPTY_FLUSH_BEGIN()                                      \
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
   __syncwarp();
-  // OPTY_DEBUG_NOSTORE (measurement aid, wrong results): 1 = no tile stores,
-  // 2 = all tile stores go to node rows 0..31 (no HBM write stream),
-  // 3 = stores without waiting for the staging buffer to be free again
-  if (ctx.lane == 0 && ctx.node < ctx.n_nodes && OPTY_DEBUG_NOSTORE != 1) {
-    opty_tma_store_2d(&ctx.tm->out[SEG], tile, Q * OPTY_C, OPTY_DEBUG_NOSTORE == 2 ? 0 : ctx.node);
-    if (OPTY_DEBUG_NOSTORE != 3) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(OPTY_NBUF - 1) : "memory");
-  }
-  __syncwarp();
-#else
-  __syncwarp();
-  const int rows = min(32, ctx.n_nodes - ctx.node);
-  for (int r = 0; r < rows; ++r) {
-    double* dst = ctx.jac + (long long)(ctx.node + r) * OPTY_K + SEGCOL0 + Q * OPTY_C;
-    const double* src = tile + r * OPTY_C;
-#pragma unroll
-    for (int c = 0; c < NCOLS; c += 32)
-      if (c + ctx.lane < NCOLS) dst[c + ctx.lane] = src[c + ctx.lane];
-  }
-  __syncwarp();
-#endif
-}
-#define OPTY_FLUSH(seg, q, buf, segcol0, ncols) opty_flush<seg, q, buf, segcol0, ncols>(ctx)
-
-// end of a group body: the warp's tile buffers are reused by its next tile
-#if OPTY_TMA_STORE
+#define OPTY_TSTORE(map, buf, off, w, col0)                                                                   \
+  if (ctx.lane == 0 && OPTY_DEBUG_NOSTORE != 1)                                                               \
+    opty_tma_store_2d(&ctx.tm->out[map], ctx.tile0 + (buf) * OPTY_TILE_DOUBLES + (off), (col0), ctx.node);
+#define OPTY_FLUSH_END() \
+  if (ctx.lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 #define OPTY_DRAIN()                                                                  \
   do {                                                                                \
     if (ctx.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); \
     __syncwarp();                                                                     \
   } while (0)
 #else
+// shapes TMA cannot describe (odd M*P): the warp copies a sub-tile out itself,
+// one node row per iteration, coalesced
+#define OPTY_PHASE_BEGIN(t) __syncwarp()
+#define OPTY_FLUSH_BEGIN() __syncwarp();
+#define OPTY_TSTORE(map, buf, off, w, col0)                                            \
+  {                                                                                    \
+    const double* src_ = ctx.tile0 + (buf) * OPTY_TILE_DOUBLES + (off);                \
+    const int rows_ = min(32, ctx.n_nodes - ctx.node);                                 \
+    for (int r_ = 0; r_ < rows_; ++r_) {                                               \
+      double* dst_ = ctx.jac + (long long)(ctx.node + r_) * OPTY_K + (col0);           \
+      for (int c_ = ctx.lane; c_ < (w); c_ += 32) dst_[c_] = src_[r_ * (w) + c_];      \
+    }                                                                                  \
+  }
+#define OPTY_FLUSH_END()
 #define OPTY_DRAIN() \
   do {               \
   } while (0)
 #endif
 
-// dynamic shared memory: [WARPS][NBUF][32][C] Jacobian tiles | [NSEG][R+D][XBOX]
-// trajectory segments | mbarrier, tile slot
+// dynamic shared memory: [WARPS][NBUF][OPTY_TILE_DOUBLES] staging buffers |
+// [NSEG][R+D][XBOX] trajectory segments | mbarrier
 #define OPTY_SMEM_TILES_BYTES (OPTY_WARPS * OPTY_NBUF * OPTY_TILE_DOUBLES * 8)
 #if OPTY_TMA_LOAD == 2
 #define OPTY_SMEM_XIN_BYTES 0
@@ -221,12 +242,13 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
 #elif OPTY_TMA_LOAD == 1
 #define OPTY_STAGE_INPUT()                                                                               \
   if (threadIdx.x == 0) {                                                                                \
+    opty_mbar_init(bar, 1);                                                                              \
     opty_mbar_expect_tx(bar, OPTY_NSEG * OPTY_RD * OPTY_XBOX * 8);                                       \
     for (int sgm = 0; sgm < OPTY_NSEG; ++sgm)                                                            \
       opty_tma_load_2d(xin_bytes + sgm * OPTY_XSEG_BYTES, &tm.in, tile_node0 + sgm * OPTY_XSEG, 0, bar); \
   }                                                                                                      \
-  opty_mbar_wait(bar, phase);                                                                            \
-  phase ^= 1u;
+  __syncthreads();                                                                                       \
+  opty_mbar_wait(bar, 0);
 #else
 #define OPTY_STAGE_INPUT()                                                                               \
   for (int sgm = 0; sgm < OPTY_NSEG; ++sgm) {                                                            \
@@ -243,59 +265,41 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
 // One block = one tile of 32*W nodes x one output group; grid = (tiles, groups).
 // blockIdx.y walks the groups in the order the emitter chose (most expensive
 // first, so that the cheap groups fill the tail of the launch); the hardware
-// block scheduler balances the SMs (measured: a persistent variant with global
-// tile counters or a static schedule loses more to scheduling round trips and
-// imbalance than it gains in instruction-cache locality).
+// block scheduler balances the SMs.
 //
 // The generated kernel body sits between OPTY_KERNEL_BEGIN and OPTY_KERNEL_END
 // and dispatches on `opty_g`.
-#ifndef OPTY_TILE_MAJOR
-#define OPTY_TILE_MAJOR 0
-#endif
-#if OPTY_TILE_MAJOR
-// tile-major dispatch: consecutive blocks are the groups of ONE node tile, so a
-// node row's 8 KB are written within a short time window (DRAM page locality of
-// the write-back stream) instead of in one phase per group
-#define OPTY_BLOCK_TO_WORK()                                                        \
-  const unsigned opty_lin = blockIdx.y * gridDim.x + blockIdx.x;                    \
-  const int opty_g = opty_group_order[opty_lin % OPTY_NGROUPS];                     \
-  const int tile_node0 = (int)(opty_lin / OPTY_NGROUPS) * OPTY_THREADS;
-#else
-#define OPTY_BLOCK_TO_WORK()                              \
-  const int opty_g = opty_group_order[blockIdx.y];        \
-  const int tile_node0 = blockIdx.x * OPTY_THREADS;
-#endif
 #define OPTY_KERNEL_BEGIN()                                                                              \
   extern __shared__ __align__(128) unsigned char opty_smem[];                                            \
   double* tiles = reinterpret_cast<double*>(opty_smem);                                                  \
   unsigned char* xin_bytes = opty_smem + OPTY_SMEM_TILES_BYTES;                                          \
   uint64_t* bar = reinterpret_cast<uint64_t*>(opty_smem + OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES);  \
-  uint32_t phase = 0;                                                                                    \
-  (void)phase;                                                                                           \
-  if (OPTY_TMA_LOAD == 1) {                                                                              \
-    if (threadIdx.x == 0) opty_mbar_init(bar, 1);                                                        \
-    __syncthreads();                                                                                     \
-  }                                                                                                      \
-  OPTY_BLOCK_TO_WORK()                                                                                   \
+  (void)bar;                                                                                             \
+  (void)xin_bytes;                                                                                       \
+  const int opty_g = opty_group_order[blockIdx.y];                                                       \
+  const int tile_node0 = blockIdx.x * OPTY_THREADS;                                                      \
   OPTY_STAGE_INPUT()                                                                                     \
   OptyCtx ctx;                                                                                           \
   ctx.lane = threadIdx.x & 31;                                                                           \
   ctx.n_nodes = p.n_nodes;                                                                               \
   ctx.ldt = p.ldt;                                                                                       \
-  if (OPTY_TMA_LOAD == 2)                                                                                \
-    ctx.xs = p.traj + min(tile_node0 + (int)threadIdx.x, p.n_nodes - 1);                                 \
-  else                                                                                                   \
-    ctx.xs = reinterpret_cast<const double*>(xin_bytes + (threadIdx.x / OPTY_XSEG) * OPTY_XSEG_BYTES) +  \
-             (threadIdx.x % OPTY_XSEG);                                                                  \
+  OPTY_CTX_INPUT()                                                                                       \
   ctx.ldc = p.ldc;                                                                                       \
   ctx.tile0 = tiles + (threadIdx.x >> 5) * OPTY_NBUF * OPTY_TILE_DOUBLES;                                \
-  ctx.trow0 = ctx.tile0 + ctx.lane * OPTY_C;                                                             \
   ctx.jac = p.jac;                                                                                       \
   ctx.tm = &tm;                                                                                          \
   ctx.node = tile_node0 + (threadIdx.x & ~31);                                                           \
   ctx.active = (tile_node0 + (int)threadIdx.x) < p.n_nodes;                                              \
   ctx.con = p.con + tile_node0 + threadIdx.x;                                                            \
   if (ctx.node >= p.n_nodes) return;
+
+#if OPTY_TMA_LOAD == 2
+#define OPTY_CTX_INPUT() ctx.xg = p.traj + min(tile_node0 + (int)threadIdx.x, p.n_nodes - 1);
+#else
+#define OPTY_CTX_INPUT()                                                                \
+  ctx.xs = opty_smem_u32(xin_bytes + (threadIdx.x / OPTY_XSEG) * OPTY_XSEG_BYTES) +    \
+           (threadIdx.x % OPTY_XSEG) * 8;
+#endif
 
 #define OPTY_KERNEL_END()
 
@@ -312,4 +316,3 @@ static __device__ __forceinline__ void opty_flush(const OptyCtx& ctx) {
   const double* xg = p.traj + node;                             \
   double* drv = p.traj + (long long)OPTY_R * p.ldt + node;      \
   const int opty_pg = blockIdx.y;
-

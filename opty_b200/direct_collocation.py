@@ -49,49 +49,42 @@ _METHODS = ('backward euler', 'midpoint')
 
 DEFAULT_CUDA_OPTIONS = {
     'groups': 'auto',           # number of output groups (grid.y) or 'auto'
-    'tile_cols': 30,            # Jacobian staging tile width (doubles)
-    'tile_bufs': 2,             # staging tiles per warp (2..4)
+    'tile_cols': 'auto',        # columns of one staging buffer: a whole
+                                # equation row up to 64 columns, else 52
+    'tile_bufs': 2,             # staging buffers per warp (1 or 2)
     'warps_per_block': 'auto',  # 2, or 8 when there are enough node tiles x
                                 # groups for >= 6 waves of 8-warp blocks (the
                                 # warps of a block share every instruction
                                 # fetch: large models are bound by that)
-    'min_blocks_per_sm': 'auto',  # 4 for 2-warp blocks, 1 for 8-warp blocks
+    'min_blocks_per_sm': 'auto',  # launch bound: 16 warps per SM
     'fmad': True,               # FMA contraction (False: mul/add stay unfused
-                                # like gcc -O2 on x86-64, residuals then match
-                                # the reference bit for bit in ~90 % of entries)
+                                # like gcc -O2 on x86-64)
     'maxrregcount': None,
     'tma_load': True,           # input staging: True = TMA tile loads into
                                 # shared memory, False = plain loads into
                                 # shared memory, 'direct' = no staging
     'tma_store': True,
     'pre_pass': True,           # shared expensive sub-expressions once per node
-    'const_runs': False,        # node-invariant column runs are replicated by
-                                # a separate kernel (own stream) instead of
-                                # being staged per node by the group bodies;
-                                # measured: no gain at config 2 (profiles/)
-    'const_run_min': 16,        # shortest run (columns) worth carving out
+    'schedule': True,           # register-pressure scheduler (schedule.py);
+                                # False: outputs in column order, temporaries
+                                # depth-first before their first use
+    'reassociate': True,        # sums accumulate their terms in arrival order
+                                # (False: the association order of the
+                                # reference's C printer is kept, results are
+                                # then independent of grouping and tiling)
+    'live_budget': 40,          # float64 values a body may keep alive before
+                                # the scheduler starts recomputing cheap ones
+    'inline_cost': 2,
+    'remat_cost': 24,
+    'fence_every': 0,           # warp-level memory fence every so many
+                                # statements (bounds ptxas' load hoisting)
     'debug_nostore': False,     # measurement aid: skip Jacobian tile stores
-    'debug_reps': 1,            # measurement aid: evaluate every tile n times
     'out_ring': 2,              # device output sets to rotate through (2: an
                                 # evaluation at a new point does not wait for
                                 # the speculative Jacobian copy of the last one)
     'use_sympy_cse': True,
     'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
     'prefetch_jacobian': True,  # constraints() starts the Jacobian D2H early
-    'max_body_cost': 0.0,       # > 0: equations whose body would cost more
-                                # are cut into column blocks.  Off by default:
-                                # at the n-link chains the first block of an
-                                # equation (residual + d/dq_j) carries 80 % of
-                                # its operations, so the largest body hardly
-                                # shrinks while the total work doubles
-    'tile_major': False,        # dispatch order of the grid kernel: the groups
-                                # of one node tile next to each other
-    'persistent': False,        # persistent main kernel: one block per SM
-                                # bound to one group, measured static schedule,
-                                # pre-pass as phase 0 of the same launch
-    'persistent_tune': 2,       # re-balancing passes of that schedule
-    'persistent_block_stores': True,  # one [32*W x C] TMA store per chunk and
-                                # block (False: one [32 x C] store per warp)
     'use_index': True,          # set-up cache keyed by the symbolic inputs
     'compile_shards': 'auto',   # modules compiled in parallel (large problems)
     'target_warps': 148 * 16,
@@ -604,7 +597,7 @@ class ConstraintCollocator(object):
 
 
 def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
-                           show_compile_output=False):
+                           show_compile_output=False, pair=None):
     """Groups, emits and compiles the CUDA module of a
     :class:`CollocationProgram` for ``num_nodes`` evaluation nodes.  Needs nvcc
     but no GPU.  Returns ``(parts, derived, source, meta, cubin, cubin_path,
@@ -624,24 +617,12 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
                              float(opts['max_group_cost'])))
         groups = max(1, g_par, g_cost)
     groups = int(min(groups, M, runtime.OPTY_MAX_GROUPS))
+    # with TMA stores a group starts at an even column (odd P: even row)
     align = 2 if tma_store else 1
-    const_runs = []
-    if opts['const_runs'] and tma_store:
-        const_runs = prog.constant_runs(min_len=int(opts['const_run_min']))
-    prog.set_carved(const_runs)
-    P = prog.P
-    max_body = float(opts['max_body_cost'])
-    min_cols = 16 if align == 2 else 15
 
     def column_parts(stop=None):
-        # balanced ranges of whole equations, then equations whose body
-        # would be too large are cut into column blocks
         rows = prog.partition_rows(groups, col_align=align, stop=stop)
-        cparts = [(r0 * P, r1 * P) for r0, r1 in rows]
-        if max_body > 0 and tma_store:
-            cparts = prog.split_heavy(cparts, max_body, col_align=align,
-                                      min_cols=min_cols, stop=stop)
-        return cparts
+        return [(r0 * prog.P, r1 * prog.P) for r0, r1 in rows]
 
     parts = column_parts()
     derived = []
@@ -650,10 +631,6 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         if derived:
             # re-balance with the shared work taken out of the groups
             parts = column_parts(stop=set(derived))
-    if len(parts) > runtime.OPTY_MAX_GROUPS:
-        raise ValueError('The problem needs {} output groups, at most {} are '
-                         'supported; raise max_body_cost.'.format(
-                             len(parts), runtime.OPTY_MAX_GROUPS))
     if prog.R + len(derived) > 256 and tma_load == 1:
         tma_load = 0
     wpb = opts['warps_per_block']
@@ -663,38 +640,33 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     wpb = int(wpb)
     mbs = opts['min_blocks_per_sm']
     if mbs == 'auto':
-        mbs = max(1, 8 // wpb)
+        mbs = max(1, 16 // wpb)
     mbs = int(mbs)
+    tile_cols = codegen.choose_tile_cols(opts['tile_cols'], prog.P,
+                                         even=tma_store)
+    tile_bufs = int(opts['tile_bufs'])
     if tma_load != 2:
-        # staged input must fit beside the Jacobian tiles in 227 KB of shared
-        # memory per block; otherwise the lanes read the trajectory matrix
-        # directly (coalesced, read-only path)
+        # staged input must fit beside the staging buffers in 227 KB of
+        # shared memory per block; otherwise the lanes read the trajectory
+        # matrix directly (coalesced, read-only path)
         threads = 32 * wpb
         xseg = min(threads, 128)
         xin = (threads // xseg) * (
             -(-((prog.R + len(derived)) * (xseg + 2) * 8) // 128) * 128)
-        tiles = (wpb * int(opts['tile_bufs']) * 32 *
-                 codegen.choose_tile_cols(opts['tile_cols']) * 8)
+        tiles = wpb * tile_bufs * 32 * tile_cols * 8
         if xin + tiles + 128 > 227 * 1024:
             tma_load = 2
 
     flags = build.module_flags(fmad=opts['fmad'],
                                maxrregcount=opts['maxrregcount'])
+    sched_opts = {k: opts[k] for k in codegen.SCHEDULE_DEFAULTS}
+    cost = prog.stats()['varying_cost']
     emit_kwargs = dict(
-        tile_cols=opts['tile_cols'],
-        warps_per_block=wpb, min_blocks_per_sm=mbs,
+        tile_cols=tile_cols, warps_per_block=wpb, min_blocks_per_sm=mbs,
         tma_load=tma_load, tma_store=tma_store, derived=derived,
-        debug_nostore=opts['debug_nostore'],
-        tile_bufs=opts['tile_bufs'], debug_reps=opts['debug_reps'],
-        const_runs=const_runs, persistent=bool(opts['persistent']),
-        tile_major=bool(opts['tile_major']),
-        persistent_block_stores=bool(opts['persistent_block_stores']))
-    if opts['persistent']:
-        if tma_load != 1 or not tma_store or const_runs:
-            raise ValueError('The persistent kernel needs TMA input staging '
-                             'and TMA stores and does not combine with '
-                             'const_runs.')
-        opts = dict(opts, compile_shards=1)
+        debug_nostore=opts['debug_nostore'], tile_bufs=tile_bufs, pair=pair,
+        schedule_options=sched_opts,
+        workers=(os.cpu_count() or 1) if cost >= 20000 else 1)
 
     # Large problems are split into several modules (contiguous ranges of
     # output groups) that nvcc compiles in parallel; the runtime launches one
@@ -703,10 +675,8 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     # the dominant set-up cost.
     shards = opts['compile_shards']
     if shards == 'auto':
-        big = prog.stats()['varying_cost'] >= 40000 and len(parts) >= 4
+        big = cost >= 40000 and len(parts) >= 4
         shards = min(len(parts), os.cpu_count() or 1, 16) if big else 1
-        # a module's TMA descriptors travel as one kernel parameter
-        shards = max(shards, -(-len(parts) // 96))
     shards = max(1, min(int(shards), len(parts)))
     if shards == 1:
         ranges = [None]
@@ -727,7 +697,7 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         bounds = [0] + cuts + [len(parts)]
         ranges = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
 
-    logger.info('Emitting the CUDA module%s.',
+    logger.info('Scheduling and emitting the CUDA module%s.',
                 '' if len(ranges) == 1 else 's ({})'.format(len(ranges)))
     emitted = []
     for i, rng in enumerate(ranges):
@@ -735,11 +705,6 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
             prog, parts, method, only_groups=rng, with_aux=(i == 0),
             **emit_kwargs))
     source, meta = emitted[0]
-    if len(meta['segments']) > runtime.OPTY_MAX_SEGMENTS:
-        raise ValueError('The module needs {} store segments, at most {} are '
-                         'supported; raise const_run_min.'.format(
-                             len(meta['segments']),
-                             runtime.OPTY_MAX_SEGMENTS))
     logger.info('Compiling the constraint and Jacobian kernels.')
 
     def compile_one(src):
@@ -757,46 +722,9 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     cache_hit = all(c[2] for c in compiled)
     meta['extra_modules'] = [
         {'cubin_path': c[1], 'group_range': e[1]['group_range'],
-         'segment_range': e[1]['segment_range'],
-         'num_groups': e[1]['num_groups'],
-         'groups': e[1]['groups']}
+         'num_groups': e[1]['num_groups'], 'groups': e[1]['groups']}
         for e, c in zip(emitted[1:], compiled[1:])]
     return parts, derived, source, meta, cubin, cubin_path, cache_hit
-
-
-def make_schedule(round_costs, n_tiles, num_blocks, warps):
-    """Static schedule of the persistent kernel: ``round_costs[g]`` is the
-    (measured or estimated) time one block needs for one round of ``warps``
-    tiles of group ``g``.  Every group gets a number of blocks -- one block
-    per SM -- such that the slowest block is as fast as possible (greedy on
-    the step function ``ceil(tiles / warps) * round_cost``), and its tiles
-    are dealt out evenly.  Returns ``[(group, first_tile, end_tile), ...]``."""
-    G = len(round_costs)
-    if G > num_blocks:
-        raise ValueError('The persistent kernel needs at most one output '
-                         'group per SM ({} groups, {} SMs).'.format(
-                             G, num_blocks))
-    blocks = [1] * G
-
-    def block_time(g):
-        tiles = -(-n_tiles // blocks[g])
-        return -(-tiles // warps) * round_costs[g]
-
-    for _ in range(num_blocks - G):
-        g = max(range(G), key=block_time)
-        if blocks[g] >= n_tiles:
-            break
-        blocks[g] += 1
-    triples = []
-    for g in range(G):
-        base, extra = divmod(n_tiles, blocks[g])
-        t0 = 0
-        for b in range(blocks[g]):
-            k = base + (1 if b < extra else 0)
-            if k:
-                triples.append((g, t0, t0 + k))
-            t0 += k
-    return triples
 
 
 def attach_extra_modules(handle, meta):
@@ -804,34 +732,7 @@ def attach_extra_modules(handle, meta):
     several pieces into ``handle``."""
     for em in meta.get('extra_modules', ()):
         with open(em['cubin_path'], 'rb') as f:
-            cubin = f.read()
-        s0, s1 = em['segment_range']
-        handle.add_module(cubin, s0, s1 - s0, em['num_groups'])
-
-
-def fill_kernel_config(cfg, meta, opts):
-    """Copies the kernel geometry of an emitted module into a ``ColloCfg``."""
-    cfg.abi_version = runtime.ABI_VERSION
-    cfg.num_inv = meta['num_inv']
-    cfg.num_groups = meta['num_groups']
-    cfg.num_derived = meta['D']
-    cfg.tile_cols = meta['C']
-    cfg.warps_per_block = meta['warps_per_block']
-    cfg.pre_groups = meta['pre_groups']
-    cfg.tile_bufs = meta['tile_bufs']
-    cfg.tma_load = int(meta['tma_load'])
-    cfg.tma_store = int(meta['tma_store'])
-    cfg.out_ring = int(opts['out_ring'])
-    cfg.prefetch_jac = int(bool(opts.get('prefetch_jacobian', False)))
-    cfg.persistent = (0 if not meta.get('persistent') else
-                      1 if meta.get('persistent_block_stores', True) else 2)
-    cfg.num_segments = len(meta['segments'])
-    seg_range = meta.get('segment_range', [0, len(meta['segments'])])
-    cfg.primary_segments = seg_range[1] - seg_range[0]
-    cfg.const_image_doubles = meta['const_image_doubles']
-    for sid, (col0, ncols) in enumerate(meta['segments']):
-        cfg.seg_col0[sid] = col0
-        cfg.seg_ncols[sid] = ncols
+            handle.add_module(f.read())
 
 
 class _PreparedModule(object):
@@ -851,7 +752,8 @@ class _PreparedModule(object):
         (self.parts, self.derived, self.source, self.meta, self.cubin,
          self.cubin_path, self.cache_hit) = prepare_program_module(
             prog, hi - lo, col.integration_method, opts, tmp_dir=col.tmp_dir,
-            show_compile_output=col.show_compile_output)
+            show_compile_output=col.show_compile_output,
+            pair=col.num_states)
         self.index_hit = False
         if key is not None and self.cubin_path:
             build.store_index(col.tmp_dir, key, {
@@ -883,17 +785,15 @@ class _PreparedModule(object):
                             for rule in col._chain_rules()]).encode())
         opts = {k: v for k, v in col._cuda_options.items()
                 if k not in ('out_ring', 'prefetch_jacobian',
-                             'd2h_skip_constants', 'persistent_tune',
-                             'use_index')}
+                             'd2h_skip_constants', 'use_index')}
         hasher.update(repr(sorted(opts.items())).encode())
         hasher.update(repr((num_nodes, col.integration_method,
                             codegen.EMITTER_VERSION)).encode())
-        hasher.update(build._header_digest(
-            '#include "colloc_persistent.cuh"').encode())
+        hasher.update(build._header_digest().encode())
         # the lowering / emitter code itself: any change invalidates the index
         here = os.path.dirname(os.path.abspath(__file__))
         for name in ('codegen.py', 'ir.py', 'lowering.py', 'program.py',
-                     'direct_collocation.py', 'build.py'):
+                     'schedule.py', 'direct_collocation.py', 'build.py'):
             with open(os.path.join(here, name), 'rb') as f:
                 hasher.update(f.read())
         return hasher.hexdigest()[:32]
@@ -967,7 +867,7 @@ class _CudaEvaluator(object):
         self.nnz_inst = nnz_inst
 
         cfg = runtime.ColloCfg()
-        fill_kernel_config(cfg, meta, opts)
+        cfg.abi_version = runtime.ABI_VERSION
         cfg.device = col._device
         cfg.N = col.num_collocation_nodes
         cfg.node_lo, cfg.node_hi = lo, hi
@@ -979,24 +879,21 @@ class _CudaEvaluator(object):
         cfg.pk = col.num_known_parameters
         cfg.M, cfg.P = M, P
         cfg.method = 1 if col.integration_method == 'midpoint' else 0
+        cfg.out_ring = int(opts['out_ring'])
+        cfg.prefetch_jac = int(bool(opts['prefetch_jacobian']))
         cfg.con_tail = o
         cfg.jac_tail = nnz_inst
         cfg.h = 0.0 if col._variable_duration else float(
             col.node_time_interval)
         self.handle = runtime.ColloHandle(cfg, cubin)
         attach_extra_modules(self.handle, meta)
-        if meta['const_runs']:
-            self.handle.set_const_runs(meta['const_runs'], meta['const_lit'],
-                                       meta['const_inv'])
         self.nn = nn
         self.con_len = M * nn
         self.jac_len = nn * K
 
-        if meta.get('persistent'):
-            self._setup_persistent_schedule(opts)
-
         self._callable_known = any(
             _is_callable_value(v) for v in col.known_trajectory_map.values())
+        self._pushed_known = None
         self._push_known(None)
 
         if opts['d2h_skip_constants']:
@@ -1004,6 +901,13 @@ class _CudaEvaluator(object):
 
     # known values -----------------------------------------------------
     def _push_known(self, free):
+        """Pushes the known parameter values and known input trajectories to
+        the device if they differ from what is there.  The maps are re-read on
+        every callback like the reference does (``_merge_fixed_free``,
+        opty/direct_collocation.py:2891-2926, called from every
+        ``constraints`` / ``jacobian``, :2973-2980): a user may change a
+        parameter between two solves.  Callables see the free vector on every
+        evaluation (opty/direct_collocation.py:2916-2917)."""
         col = self.col
         N = col.num_collocation_nodes
         traj = None
@@ -1012,57 +916,19 @@ class _CudaEvaluator(object):
             for i, sym in enumerate(col.known_input_trajectories):
                 val = col.known_trajectory_map[sym]
                 if _is_callable_value(val):
-                    # callables see the free vector on every evaluation
-                    # (opty/direct_collocation.py:2916-2917)
                     val = val(np.ones(col.num_free) if free is None else free)
                 traj[i] = val
         params = None
         if col.num_known_parameters:
             params = np.array([float(col.known_parameter_map[p])
                                for p in col.known_parameters])
+        last = self._pushed_known
+        if last is not None and \
+                (traj is None or np.array_equal(traj, last[0])) and \
+                (params is None or np.array_equal(params, last[1])):
+            return
         self.handle.set_known(traj, params)
-
-    def _setup_persistent_schedule(self, opts):
-        """Initial schedule from the emitter's cost model; it is re-balanced
-        from measured block times on the first evaluations
-        (:meth:`tune_schedule`)."""
-        import torch
-        meta = self.meta
-        self._sched_sms = torch.cuda.get_device_properties(
-            self.col._device).multi_processor_count
-        self._sched_warps = meta['warps_per_block']
-        self._sched_tiles = -(-self.nn // 32)
-        self._round_costs = [20.0 * g['ops'] + 43.0 * g['ncols']
-                             for g in meta['groups']]
-        self._sched = make_schedule(self._round_costs, self._sched_tiles,
-                                    self._sched_sms, self._sched_warps)
-        self.handle.set_schedule(self._sched)
-        self._tune_left = int(opts['persistent_tune'])
-
-    def tune_schedule(self, evals=3):
-        """One re-balancing pass: times ``evals`` evaluations of the resident
-        free vector, converts every block's clock count into a per-round cost
-        of its group and rebuilds the schedule."""
-        h = self.handle
-        W = self._sched_warps
-        acc = np.zeros(len(self._round_costs))
-        cnt = np.zeros(len(self._round_costs))
-        for _ in range(evals):
-            h.eval_device(sync=True)
-            clocks = h.block_clocks()
-            for (g, t0, t1), c in zip(self._sched, clocks):
-                rounds = -(-(t1 - t0) // W)
-                acc[g] += c / rounds
-                cnt[g] += 1
-        self._round_costs = list(acc / np.maximum(cnt, 1))
-        self._sched = make_schedule(self._round_costs, self._sched_tiles,
-                                    self._sched_sms, W)
-        h.set_schedule(self._sched)
-
-    def _maybe_tune(self):
-        while getattr(self, '_tune_left', 0) > 0:
-            self._tune_left -= 1
-            self.tune_schedule()
+        self._pushed_known = (traj, params)
 
     def _setup_constant_elision(self):
         """Jacobian columns whose value cannot change between calls --
@@ -1108,23 +974,20 @@ class _CudaEvaluator(object):
 
     def constraints(self, free):
         free = self._check_free(free)
-        if self._callable_known:
-            self._push_known(free)
-        if getattr(self, '_tune_left', 0) > 0:
-            self.handle.upload_free(free)
-            self._maybe_tune()
+        self._push_known(free)
         buf = self.handle.constraints(free)
         if self.num_inst:
             buf[self.con_len:] = self.col.eval_instance_constraints(free)
         return buf.copy()
 
-    def jacobian(self, free):
+    def jacobian(self, free, refetch=False):
+        """``refetch=True`` copies the whole Jacobian block from the device
+        again, including the columns that cannot have changed (see
+        :meth:`Problem.jacobian`)."""
         free = self._check_free(free)
-        if self._callable_known:
-            self._push_known(free)
-        if getattr(self, '_tune_left', 0) > 0:
-            self.handle.upload_free(free)
-            self._maybe_tune()
+        self._push_known(free)
+        if refetch:
+            self.handle.invalidate_host_jacobian()
         buf = self.handle.jacobian(free)
         if self.num_inst:
             buf[self.jac_len:] = \

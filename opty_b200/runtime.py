@@ -13,24 +13,26 @@ import numpy as np
 from . import build
 
 OPTY_MAX_GROUPS = 1024
-OPTY_MAX_SEGMENTS = 1024
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 EXPORTS = (
     'opty_b200_abi_version', 'opty_colloc_create', 'opty_colloc_destroy',
-    'opty_colloc_set_known', 'opty_colloc_upload_free',
-    'opty_colloc_eval_device', 'opty_colloc_constraints',
-    'opty_colloc_jacobian', 'opty_colloc_host_buffers',
+    'opty_colloc_add_module', 'opty_colloc_set_known',
+    'opty_colloc_upload_free', 'opty_colloc_eval_device',
+    'opty_colloc_constraints', 'opty_colloc_jacobian', 'opty_colloc_begin',
+    'opty_colloc_finish', 'opty_colloc_set_host_outputs', 'opty_host_alloc',
+    'opty_host_free', 'opty_colloc_host_buffers',
     'opty_colloc_device_buffers', 'opty_colloc_set_d2h_columns',
-    'opty_colloc_set_const_runs', 'opty_colloc_add_module',
-    'opty_colloc_set_schedule', 'opty_colloc_block_clocks',
+    'opty_colloc_invalidate_host_jacobian', 'opty_colloc_quadrature',
     'opty_colloc_last_kernel_ms', 'opty_colloc_time_device_evals',
-    'opty_colloc_launch_count',
-    'opty_colloc_jacobian_indices', 'opty_colloc_last_error',
+    'opty_colloc_launch_count', 'opty_colloc_jacobian_indices',
+    'opty_colloc_last_error',
 )
 
 
 class ColloCfg(ctypes.Structure):
+    """``opty_colloc_cfg`` of include/opty_b200.h: the problem in the
+    reference's notation; no kernel geometry."""
     _fields_ = [
         ('abi_version', ctypes.c_int32),
         ('device', ctypes.c_int32),
@@ -46,25 +48,10 @@ class ColloCfg(ctypes.Structure):
         ('M', ctypes.c_int32),
         ('P', ctypes.c_int32),
         ('method', ctypes.c_int32),
-        ('num_inv', ctypes.c_int32),
-        ('num_groups', ctypes.c_int32),
-        ('num_derived', ctypes.c_int32),
-        ('tile_cols', ctypes.c_int32),
-        ('warps_per_block', ctypes.c_int32),
-        ('pre_groups', ctypes.c_int32),
-        ('tile_bufs', ctypes.c_int32),
-        ('tma_load', ctypes.c_int32),
-        ('tma_store', ctypes.c_int32),
         ('out_ring', ctypes.c_int32),
+        ('prefetch_jac', ctypes.c_int32),
         ('con_tail', ctypes.c_int32),
         ('jac_tail', ctypes.c_int32),
-        ('prefetch_jac', ctypes.c_int32),
-        ('persistent', ctypes.c_int32),
-        ('num_segments', ctypes.c_int32),
-        ('primary_segments', ctypes.c_int32),
-        ('const_image_doubles', ctypes.c_int32),
-        ('seg_col0', ctypes.c_int32 * OPTY_MAX_SEGMENTS),
-        ('seg_ncols', ctypes.c_int32 * OPTY_MAX_SEGMENTS),
         ('h', ctypes.c_double),
     ]
 
@@ -104,14 +91,17 @@ def load_library(path=None):
         c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(ctypes.c_int64),
         ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]
     lib.opty_colloc_set_d2h_columns.argtypes = [c_vp, ctypes.c_int, c_vp,
-                                                c_vp, c_vp]
-    lib.opty_colloc_add_module.argtypes = [c_vp, c_vp, ctypes.c_size_t,
-                                           ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_int]
-    lib.opty_colloc_set_schedule.argtypes = [c_vp, ctypes.c_int, c_vp]
-    lib.opty_colloc_block_clocks.argtypes = [c_vp, ctypes.c_int, c_vp]
-    lib.opty_colloc_set_const_runs.argtypes = [c_vp, ctypes.c_int, c_vp, c_vp,
-                                               c_vp, c_vp]
+                                                c_vp]
+    lib.opty_colloc_invalidate_host_jacobian.argtypes = [c_vp]
+    lib.opty_colloc_add_module.argtypes = [c_vp, c_vp, ctypes.c_size_t]
+    lib.opty_colloc_begin.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int]
+    lib.opty_colloc_finish.argtypes = [c_vp]
+    lib.opty_colloc_set_host_outputs.argtypes = [c_vp, c_vp, c_vp]
+    lib.opty_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(c_vp)]
+    lib.opty_host_free.argtypes = [c_vp]
+    lib.opty_colloc_quadrature.argtypes = [
+        c_vp, c_vp, ctypes.c_double, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_double), c_vp]
     lib.opty_colloc_last_kernel_ms.argtypes = [c_vp,
                                                ctypes.POINTER(ctypes.c_float)]
     lib.opty_colloc_time_device_evals.argtypes = [
@@ -260,51 +250,51 @@ class ColloHandle(object):
         return {'traj': traj.value, 'ldt': ldt.value, 'con': con.value,
                 'jac': jac.value, 'uni': uni.value}
 
-    def set_d2h_columns(self, ranges, fill=None):
+    def set_d2h_columns(self, ranges):
         n = len(ranges)
         b = (ctypes.c_int32 * max(n, 1))(*[r[0] for r in ranges])
         e = (ctypes.c_int32 * max(n, 1))(*[r[1] for r in ranges])
-        fp = None
-        if fill is not None:
-            fill = _as_f64(fill, self.K, 'fill')
-            fp = fill.ctypes.data
         _check(self.lib, self.lib.opty_colloc_set_d2h_columns(
             self._h, n, ctypes.cast(b, ctypes.c_void_p),
-            ctypes.cast(e, ctypes.c_void_p), fp))
+            ctypes.cast(e, ctypes.c_void_p)))
 
-    def add_module(self, cubin, seg_first, seg_count, num_groups):
+    def invalidate_host_jacobian(self):
+        _check(self.lib, self.lib.opty_colloc_invalidate_host_jacobian(
+            self._h))
+
+    def add_module(self, cubin):
         buf = ctypes.create_string_buffer(cubin, len(cubin))
         self._extra_cubins = getattr(self, '_extra_cubins', []) + [buf]
         _check(self.lib, self.lib.opty_colloc_add_module(
-            self._h, ctypes.cast(buf, ctypes.c_void_p), len(cubin),
-            int(seg_first), int(seg_count), int(num_groups)))
+            self._h, ctypes.cast(buf, ctypes.c_void_p), len(cubin)))
 
-    def set_schedule(self, triples):
-        """``triples``: one ``(group, first_tile, end_tile)`` per block of the
-        persistent kernel."""
-        arr = np.ascontiguousarray(triples, dtype=np.int32).reshape(-1, 3)
-        _check(self.lib, self.lib.opty_colloc_set_schedule(
-            self._h, arr.shape[0], arr.ctypes.data))
-        self._sched_blocks = arr.shape[0]
+    def set_host_outputs(self, con_full, jac_full):
+        """Redirects this handle's device->host copies into its slices of
+        full-problem host vectors (``PinnedArray`` or None, None)."""
+        cp = None if con_full is None else con_full.ctypes.data
+        jp = None if jac_full is None else jac_full.ctypes.data
+        _check(self.lib, self.lib.opty_colloc_set_host_outputs(self._h, cp,
+                                                               jp))
 
-    def block_clocks(self):
-        out = np.zeros(self._sched_blocks, dtype=np.int64)
-        _check(self.lib, self.lib.opty_colloc_block_clocks(
-            self._h, self._sched_blocks, out.ctypes.data))
-        return out
+    def begin(self, free, want_con, want_jac):
+        """``free`` must stay alive until :meth:`finish`."""
+        _check(self.lib, self.lib.opty_colloc_begin(
+            self._h, free.ctypes.data, int(want_con), int(want_jac)))
 
-    def set_const_runs(self, runs, lit, inv_idx):
-        """``runs``: list of ``(col0, length)``; ``lit`` / ``inv_idx``: the
-        pattern of all runs concatenated."""
-        col0 = np.array([r[0] for r in runs], dtype=np.int32)
-        length = np.array([r[1] for r in runs], dtype=np.int32)
-        lit = np.ascontiguousarray(lit, dtype=np.float64)
-        inv_idx = np.ascontiguousarray(inv_idx, dtype=np.int32)
-        if len(lit) != int(length.sum()) or len(inv_idx) != len(lit):
-            raise ValueError('pattern length does not match the runs')
-        _check(self.lib, self.lib.opty_colloc_set_const_runs(
-            self._h, len(runs), col0.ctypes.data, length.ctypes.data,
-            lit.ctypes.data, inv_idx.ctypes.data))
+    def finish(self):
+        _check(self.lib, self.lib.opty_colloc_finish(self._h))
+
+    def quadrature(self, free, scale, rule):
+        """``(value, grad)`` of the running-cost integral; ``grad`` has one
+        entry per array argument and node followed by one per scalar
+        argument."""
+        free = _as_f64(free, self.free_len, 'free')
+        value = ctypes.c_double()
+        grad = np.empty(self.cfg.n * self.cfg.N + self.cfg.r)
+        _check(self.lib, self.lib.opty_colloc_quadrature(
+            self._h, free.ctypes.data, float(scale), int(rule),
+            ctypes.byref(value), grad.ctypes.data))
+        return value.value, grad
 
     def last_kernel_ms(self):
         ms = ctypes.c_float()
@@ -325,6 +315,34 @@ class ColloHandle(object):
         _check(self.lib, self.lib.opty_colloc_launch_count(
             self._h, ctypes.byref(cnt)))
         return cnt.value
+
+
+class PinnedArray(object):
+    """Page-locked, device-portable float64 host vector (``opty_host_alloc``)
+    with a NumPy view ``.array``."""
+
+    def __init__(self, count):
+        self.lib = load_library()
+        ptr = ctypes.c_void_p()
+        _check(self.lib, self.lib.opty_host_alloc(max(int(count), 1) * 8,
+                                                  ctypes.byref(ptr)))
+        self._ptr = ptr
+        buf = (ctypes.c_double * int(count)).from_address(ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=int(count))
+        self.ctypes = self.array.ctypes
+
+    def close(self):
+        if getattr(self, '_ptr', None):
+            self.array = None
+            self.ctypes = None
+            self.lib.opty_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def jacobian_indices(device, N, node_lo, node_hi, n, q, r, s, M, method):

@@ -19,7 +19,7 @@ reference raise ImportError, opty/tests/test_utils.py:301-336) are fine.
 import numpy as np
 
 from . import runtime
-from .direct_collocation import (DEFAULT_CUDA_OPTIONS, fill_kernel_config,
+from .direct_collocation import (DEFAULT_CUDA_OPTIONS,
                                  prepare_program_module,
                                  attach_extra_modules)
 from .program import CollocationProgram
@@ -51,7 +51,10 @@ def ufuncify_matrix(args, expr, const=None, tmp_dir=None, parallel=False,
                     prog, n, 'elementwise', opts, tmp_dir=tmp_dir,
                     show_compile_output=show_compile_output)
             cfg = runtime.ColloCfg()
-            fill_kernel_config(cfg, meta, opts)
+            cfg.abi_version = runtime.ABI_VERSION
+            cfg.out_ring = int(opts['out_ring'])
+            cfg.prefetch_jac = 0
+            cfg.con_tail = cfg.jac_tail = 0
             cfg.device = int(device)
             cfg.N = n
             cfg.node_lo, cfg.node_hi = 0, n
@@ -63,9 +66,6 @@ def ufuncify_matrix(args, expr, const=None, tmp_dir=None, parallel=False,
             cfg.h = 0.0
             h = runtime.ColloHandle(cfg, cubin)
             attach_extra_modules(h, meta)
-            if meta['const_runs']:
-                h.set_const_runs(meta['const_runs'], meta['const_lit'],
-                                 meta['const_inv'])
             h.set_known(None, None)
             handles[n] = h
         return h

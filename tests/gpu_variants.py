@@ -1,0 +1,38 @@
+"""Kernel-option variants exercised by the GPU suite.  Kept in one place so
+that ``__graft_entry__.build()`` can compile exactly these modules into the
+in-tree cache before the snapshot travels to the GPU box."""
+
+# tests/test_gpu_parity.py::test_config2_kernel_variants_agree_bitwise
+# (every variant additionally gets fmad=False, reassociate=False)
+CONFIG2_VARIANTS = [
+    {'groups': 1},
+    {'schedule': False, 'groups': 8},
+    {'groups': 11, 'tile_cols': 14, 'warps_per_block': 4,
+     'min_blocks_per_sm': 2, 'live_budget': 24},
+    {'tma_store': False, 'tma_load': False, 'groups': 5},
+    {'d2h_skip_constants': False, 'groups': 3, 'out_ring': 3,
+     'tile_bufs': 1, 'min_blocks_per_sm': 3, 'live_budget': 100},
+    {'pre_pass': False, 'groups': 8, 'warps_per_block': 1,
+     'min_blocks_per_sm': 8},
+    # direct input loads, one staging buffer per warp holding two rows
+    {'groups': 8, 'tma_load': 'direct', 'tile_cols': 92, 'tile_bufs': 1,
+     'warps_per_block': 1, 'min_blocks_per_sm': 8},
+    # the problem compiled as three modules (parallel nvcc runs)
+    {'compile_shards': 3, 'groups': 8, 'out_ring': 2},
+    # 8-warp blocks with direct input loads
+    {'groups': 8, 'warps_per_block': 8, 'min_blocks_per_sm': 1,
+     'tma_load': 'direct', 'compile_shards': 2},
+]
+BITWISE = {'fmad': False, 'reassociate': False}
+
+# tests/test_gpu_parity.py::test_config4_standin_against_oracle
+CONFIG4_VARIANTS = [
+    {},
+    # odd P (27): a staging buffer holds two equation rows; here cut further
+    {'tile_cols': 20, 'groups': 4, 'tile_bufs': 1},
+    {'schedule': False, 'tma_load': 'direct'},
+]
+CONFIG4_IDS = ['default', 'narrow_tiles', 'unscheduled']
+
+# tests/test_gpu_parity.py::test_node_range_shards_reproduce_the_whole
+CONFIG2_SHARD_BOUNDS = [0, 1, 2500, 7001, 9999]

@@ -85,18 +85,4 @@ def host_evaluate(collocator, free, known_traj=None):
     lib.host_eval.argtypes = [dp, dp, ctypes.c_longlong, ctypes.c_int, dp, dp]
     lib.host_eval(uni.ctypes.data_as(dp), traj.ctypes.data_as(dp), N, nn,
                   con.ctypes.data_as(dp), jac.ctypes.data_as(dp))
-    # constant column runs are replicated by the runtime's own kernel on the
-    # GPU; here from the emitted pattern and the invariants table
-    if meta['const_runs']:
-        ci = np.zeros(max(meta['num_inv'], 1))
-        lib.host_get_invariants.argtypes = [dp]
-        lib.host_get_invariants(ci.ctypes.data_as(dp))
-        lit = np.array(meta['const_lit'])
-        inv = np.array(meta['const_inv'])
-        pattern = np.where(inv >= 0, ci[np.maximum(inv, 0)], lit)
-        block = jac.reshape(nn, prog.K)
-        off = 0
-        for a, ln in meta['const_runs']:
-            block[:, a:a + ln] = pattern[off:off + ln]
-            off += ln
     return con, jac

@@ -30,7 +30,7 @@ static double opty_ci[OPTY_NINV];
 
 struct OptyCtx {
   const double* xs; long long ldt; double* con; long long ldc; double* jac;
-  int node; double tile[4][OPTY_C];
+  int node; double tile[OPTY_NBUF][OPTY_TILE_DOUBLES / 32];
 };
 
 static inline double opty_sign(double x) { return (double)((x > 0.0) - (x < 0.0)); }
@@ -39,10 +39,15 @@ static inline double opty_sign(double x) { return (double)((x > 0.0) - (x < 0.0)
 #define XB(r) ctx.xs[(long long)(r) * ctx.ldt + 1]
 #define XD(d) ctx.xs[(long long)(OPTY_R + (d)) * ctx.ldt]
 #define OPTY_CON(j, val) ctx.con[(long long)(j) * ctx.ldc] = (val)
-#define OPTY_JS2(buf, tc, v0, v1) do { const_cast<OptyCtx&>(ctx).tile[buf][tc] = (v0); const_cast<OptyCtx&>(ctx).tile[buf][(tc) + 1] = (v1); } while (0)
-#define OPTY_JS1(buf, tc, v0) const_cast<OptyCtx&>(ctx).tile[buf][tc] = (v0)
-#define OPTY_FLUSH(seg, q, buf, segcol0, ncols) \
-  memcpy(ctx.jac + (long long)ctx.node * OPTY_K + (segcol0) + (q) * OPTY_C, ctx.tile[buf], (ncols) * sizeof(double))
+// one node per "warp": a sub-tile that starts `off` doubles into the 32-lane buffer starts off/32 here
+#define OPTY_JS2(buf, off, w, c, v0, v1) do { double* t_ = const_cast<OptyCtx&>(ctx).tile[buf] + (off) / 32 + (c); t_[0] = (v0); t_[1] = (v1); } while (0)
+#define OPTY_JS1(buf, off, w, c, v0) const_cast<OptyCtx&>(ctx).tile[buf][(off) / 32 + (c)] = (v0)
+#define OPTY_PHASE_BEGIN(t) do { } while (0)
+#define OPTY_FENCE() do { } while (0)
+#define OPTY_FLUSH_BEGIN()
+#define OPTY_TSTORE(map, buf, off, w, col0) \
+  memcpy(ctx.jac + (long long)ctx.node * OPTY_K + (col0), ctx.tile[buf] + (off) / 32, (w) * sizeof(double));
+#define OPTY_FLUSH_END()
 #define OPTY_DRAIN() do { } while (0)
 #define OPTY_THREADS 1
 #define OPTY_PRE_THREADS 1

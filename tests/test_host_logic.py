@@ -319,31 +319,101 @@ def test_emitted_code_matches_reference_golden(name, make, groups):
 
 @pytest.mark.parametrize('name,make', HARNESS_WORKLOADS[2:],
                          ids=[f[0] for f in HARNESS_WORKLOADS[2:]])
-def test_column_block_groups_match_reference_golden(name, make):
-    """Equations whose body is too large are cut into column blocks
-    (``max_body_cost``); with constant runs carved out on top the blocks,
-    store segments and residual ownership must still cover every entry."""
+def test_narrow_staging_buffers_and_schedule_options(name, make):
+    """Rows wider than the staging buffer are cut into phases that pair the
+    partials with respect to a state at both nodes of the stencil; tight
+    rematerialisation budgets, the tape's own association order and the
+    unscheduled emission order must all still produce every entry."""
     gold = load_golden(name)
-    for opts in ({'groups': 2, 'max_body_cost': 150.0},
-                 {'groups': 3, 'max_body_cost': 90.0, 'const_runs': True,
-                  'const_run_min': 4}):
+    for opts in ({'groups': 2, 'tile_cols': 12, 'live_budget': 12},
+                 {'groups': 3, 'tile_cols': 20, 'reassociate': False,
+                  'tile_bufs': 1},
+                 {'groups': 2, 'schedule': False, 'tile_cols': 16},
+                 {'groups': 1, 'live_budget': 8, 'remat_cost': 60}):
         w = make()      # the seeded free vector continues the workload's rng
         col = ConstraintCollocator(*w.collocator_args(),
                                    **w.collocator_kwargs(), cuda_options=opts)
         free = w.free(col.num_free)
         from host_harness import _prepare_without_nvcc
         prog, source, meta = _prepare_without_nvcc(col)
-        P = prog.P
         cols = [g['cols'] for g in meta['groups']]
         assert cols[0][0] == 0 and cols[-1][1] == prog.K
         assert all(a[1] == b[0] for a, b in zip(cols, cols[1:]))
-        # at least one equation really was cut inside a row
-        assert any(c0 % P or c1 % P for c0, c1 in cols)
+        if 'tile_cols' in opts:
+            assert max(g['phases'] for g in meta['groups']) > \
+                (cols[0][1] - cols[0][0]) // prog.P
         con, jac = host_evaluate(col, free)
         M = col.num_eom
         nn = col.num_collocation_nodes - 1
         assert_values_close(con, gold['con'][:M * nn])
-        assert_values_close(jac, gold['jac'][:nn * M * P], row_len=P)
+        assert_values_close(jac, gold['jac'][:nn * M * prog.P],
+                            row_len=prog.P)
+
+
+def test_row_phases_cover_every_column_once():
+    from opty_b200.codegen import row_phases
+    for col0, ncols, tile, pair, even in (
+            (0, 46, 46, 22, True), (92, 206, 52, 102, True),
+            (0, 206, 52, 102, True), (86, 86, 52, 42, True),
+            (0, 27, 20, 10, False), (54, 54, 20, None, True),
+            (0, 45, 64, 19, False), (10, 30, 8, 15, True)):
+        phases = row_phases(col0, ncols, tile, pair, even)
+        seen = []
+        for ph in phases:
+            assert sum(w for _, w in ph) <= tile
+            for c0, w in ph:
+                assert w >= 1
+                if even:
+                    assert w % 2 == 0
+                seen.extend(range(c0, c0 + w))
+        assert sorted(seen) == list(range(col0, col0 + ncols)), (col0, ncols)
+    # wide rows keep the two partials of a state in one phase
+    phases = row_phases(0, 206, 52, 102, True)
+    for ph in phases[:-1]:
+        (a0, wa), (b0, wb) = ph[0], ph[1]
+        assert b0 - a0 == 102 and wa == wb
+
+
+def test_scheduler_reduces_live_values_and_keeps_every_operation():
+    """schedule.py on the heaviest equation of the 10-link pendulum: every
+    output is produced once, no value is read before it exists, and the peak
+    number of live values is a fraction of the plain emission order's."""
+    from opty_b200 import schedule
+    w = workloads.n_link_pendulum(10, 40, seed=7)
+    col = ConstraintCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    prog = col._build_program()
+    T = prog.tape
+    j = prog.M // 2 + 1
+    outs = [prog.con[j]] + list(prog.jac[j])
+    plain = schedule.plain_order(T, outs)
+    for kw in ({}, {'reassociate': False}, {'live_budget': 16},
+               {'remat_cost': 0}):
+        sc = schedule.schedule_body(T, outs, **kw)
+        dag = sc.dag
+        assert sorted(e[1] for e in sc.events if e[0] == schedule.OUT) == \
+            list(range(len(outs)))
+        have = set()
+        started = set()
+        for e in sc.events:
+            if e[0] in (schedule.OP, schedule.LOAD):
+                assert all(o in have for o in dag.rops[e[1]])
+                assert e[1] not in have
+                have.add(e[1])
+            elif e[0] == schedule.ACC:
+                s_, j_ = e[1], e[2]
+                assert all(o in have for o in dag.term_rops[s_][j_])
+                assert (s_ not in started) == bool(e[3])
+                started.add(s_)
+                if all(x in have for tr in dag.term_rops[s_] for x in tr):
+                    have.add(s_)
+            else:
+                assert all(o in have for o in dag.out_rops[e[1]])
+        assert schedule.peak_live(dag, sc.events) == sc.peak_live
+        assert sc.peak_live < 0.6 * plain.peak_live
+    tight = schedule.schedule_body(T, outs, live_budget=16)
+    loose = schedule.schedule_body(T, outs, live_budget=200)
+    assert tight.peak_live < loose.peak_live
+    assert tight.num_ops >= loose.num_ops
 
 
 @pytest.mark.parametrize('case', cases.product_cases(),
@@ -385,24 +455,13 @@ def test_module_compiles_for_sm100a_and_is_cached():
         assert 'UTMASTG' not in sass2 and 'UTMALDG' not in sass2
 
 
-def test_persistent_and_sharded_modules_compile_for_sm100a():
-    """Compile-only checks (no GPU): the persistent variant carries the TMA
-    paths and its grid barrier; a sharded build yields one module per group
-    range and only the first one holds the auxiliary kernels."""
+def test_sharded_modules_compile_for_sm100a_and_carry_their_geometry():
+    """Compile-only checks (no GPU): a sharded build yields one module per
+    group range, only the first one holds the auxiliary kernels, and every
+    module exports the ``opty_module_info`` table the runtime reads its
+    kernel geometry from (nothing of it crosses the C-ABI)."""
     w = workloads.n_link_pendulum(10, 40, seed=7)
     with tempfile.TemporaryDirectory() as tmp:
-        col = ConstraintCollocator(
-            *w.collocator_args(), **w.collocator_kwargs(), tmp_dir=tmp,
-            cuda_options={'persistent': True, 'groups': 4,
-                          'warps_per_block': 4, 'min_blocks_per_sm': 1})
-        pm = col.prepare_module()
-        assert pm.meta['persistent'] and not pm.meta['extra_modules']
-        sass = subprocess.run(['cuobjdump', '-sass', pm.cubin_path],
-                              capture_output=True, text=True).stdout
-        assert 'UTMALDG' in sass and 'UTMASTG' in sass
-        assert 'ATOM' in sass or 'RED' in sass       # grid barrier arrive
-        assert 'OptyPersist ps' in pm.source
-
         col = ConstraintCollocator(
             *w.collocator_args(), **w.collocator_kwargs(), tmp_dir=tmp,
             cuda_options={'groups': 6, 'compile_shards': 3})
@@ -412,15 +471,23 @@ def test_persistent_and_sharded_modules_compile_for_sm100a():
         ranges = [pm.meta['group_range']] + [e['group_range'] for e in extra]
         assert ranges[0][0] == 0 and ranges[-1][1] == len(pm.parts)
         assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
-        segs = [pm.meta['segment_range']] + [e['segment_range']
-                                             for e in extra]
-        assert segs[0][0] == 0 and segs[-1][1] == len(pm.meta['segments'])
+        syms = subprocess.run(['cuobjdump', '-elf', pm.cubin_path],
+                              capture_output=True, text=True).stdout
+        assert 'opty_module_info' in syms and 'opty_colloc_pre' in syms
         for e in extra:
             syms = subprocess.run(['cuobjdump', '-elf', e['cubin_path']],
                                   capture_output=True, text=True).stdout
             assert 'opty_colloc_eval' in syms
+            assert 'opty_module_info' in syms
             assert 'opty_colloc_pre' not in syms
             assert 'opty_colloc_inv' not in syms
+        # registers: the scheduled bodies fit 16 resident warps per SM
+        # without spilling
+        res = subprocess.run(['cuobjdump', '-res-usage', pm.cubin_path],
+                             capture_output=True, text=True).stdout
+        line = [ln for ln in res.splitlines() if 'REG:' in ln][0]
+        regs = int(re.search(r'REG:(\d+)', line).group(1))
+        assert regs <= 128 and 'LOCAL:0' in line
 
 
 def test_setup_index_skips_the_symbolic_work_and_tracks_its_inputs():
@@ -472,28 +539,6 @@ def test_compile_failure_raises_import_error():
         assert 'STDERR' in str(err.value)
 
 
-def test_persistent_schedule_covers_every_tile_once():
-    from opty_b200.direct_collocation import make_schedule
-    for costs, tiles, sms, warps in (([5.0, 1.0, 3.0], 313, 148, 8),
-                                     ([1.0] * 11, 40, 16, 4),
-                                     ([2.0, 9.0], 3, 148, 8)):
-        sched = make_schedule(costs, tiles, sms, warps)
-        assert len(sched) <= sms
-        seen = {}
-        for g, t0, t1 in sched:
-            assert 0 <= t0 < t1 <= tiles
-            for t in range(t0, t1):
-                assert (g, t) not in seen
-                seen[(g, t)] = 1
-        assert len(seen) == len(costs) * tiles
-    # expensive groups get more blocks than cheap ones
-    sched = make_schedule([5.0, 1.0, 3.0], 313, 148, 8)
-    blocks = [sum(1 for s in sched if s[0] == g) for g in range(3)]
-    assert blocks[0] > blocks[2] > blocks[1]
-    with pytest.raises(ValueError):
-        make_schedule([1.0] * 200, 10, 148, 8)
-
-
 def test_c_abi_library_exports_every_declared_symbol():
     lib = runtime.load_library()
     header = open(os.path.join(ROOT, 'include', 'opty_b200.h')).read()
@@ -507,7 +552,7 @@ def test_c_abi_library_exports_every_declared_symbol():
 def test_c_abi_config_struct_layout_matches_header():
     src = ('#include "opty_b200.h"\n#include <stdio.h>\n#include <stddef.h>\n'
            'int main(void){printf("%zu %zu %zu", sizeof(opty_colloc_cfg), '
-           'offsetof(opty_colloc_cfg, seg_col0), '
+           'offsetof(opty_colloc_cfg, jac_tail), '
            'offsetof(opty_colloc_cfg, h)); return 0;}')
     with tempfile.TemporaryDirectory() as tmp:
         c = os.path.join(tmp, 'sz.c')
@@ -518,7 +563,8 @@ def test_c_abi_config_struct_layout_matches_header():
         out = subprocess.run([exe], capture_output=True, text=True).stdout
     size, off_g, off_h = (int(v) for v in out.split())
     assert size == ctypes.sizeof(runtime.ColloCfg)
-    assert off_g == runtime.ColloCfg.seg_col0.offset
+    assert off_g == runtime.ColloCfg.jac_tail.offset
+    assert size <= 96      # the problem in the reference's notation, nothing else
     assert off_h == runtime.ColloCfg.h.offset
 
 

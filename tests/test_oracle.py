@@ -110,3 +110,71 @@ def test_forward_jacobian_matches_sympy_diff():
     for sym, sub in reversed(repl):
         full = full.xreplace({sym: sub})
     assert sm.simplify(full - expr.jacobian(wrt)) == sm.zeros(2, 3)
+
+
+# ---------------------------------------------------------------------------
+# second oracle: the reference's backend='numpy' path
+# ---------------------------------------------------------------------------
+NUMPY_FIXTURES = [
+    ('cfg1_pendulum_swing_up_N51_numpy_backend',
+     lambda: workloads.pendulum_swing_up(51)),
+    ('cfg3_vyasarayani2011_N101_odd_numpy_backend',
+     lambda: workloads.vyasarayani2011(101, seed=5)),
+    ('cfg4_standin_pendulum4_torques_N30_numpy_backend',
+     lambda: workloads.n_link_pendulum_torques(4, 30)),
+    ('cfg2_small_pendulum10_N12_numpy_backend',
+     lambda: workloads.n_link_pendulum(10, 12, seed=7)),
+]
+
+
+@pytest.mark.parametrize('name,make', NUMPY_FIXTURES,
+                         ids=[f[0] for f in NUMPY_FIXTURES])
+def test_lambdify_oracle_matches_reference_numpy_backend(name, make):
+    """The second oracle reproduces the outputs of the reference run with
+    backend='numpy' (tests/golden/make_golden_numpy.py) bit for bit, and the
+    two oracles -- different differentiation, different evaluator -- agree
+    to 1e-10 between themselves."""
+    from oracle.lambdify_oracle import LambdifyOracle
+    gold = load_golden(name)
+    w = make()
+    lam = LambdifyOracle(*w.collocator_args(), **w.collocator_kwargs())
+    free = w.free(lam.num_free)
+    assert np.array_equal(free, gold['free'])
+    con = lam.constraints(free)
+    jac = lam.jacobian(free)
+    assert np.array_equal(con, gold['con'])
+    assert np.array_equal(jac, gold['jac'])
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    nnz_colloc = (lam.N - 1) * lam.M * lam.P
+    assert_values_close(orc.constraints(free), con)
+    ojac = orc.jacobian(free)
+    assert_values_close(ojac[:nnz_colloc], jac[:nnz_colloc], row_len=lam.P)
+    assert_values_close(ojac[nnz_colloc:], jac[nnz_colloc:])
+
+
+def test_lambdify_oracle_sampled_entries_agree_with_full_evaluation():
+    """``jacobian_entries`` / ``residual_entries`` (the sampled form used for
+    the 20- and 50-link chains) give the same numbers as the full evaluation,
+    in float64 and -- to rounding -- in 40-digit arithmetic."""
+    from oracle.lambdify_oracle import LambdifyOracle
+    w = workloads.n_link_pendulum_torques(4, 30)
+    lam = LambdifyOracle(*w.collocator_args(), **w.collocator_kwargs())
+    free = w.free(lam.num_free)
+    M, P, nn = lam.M, lam.P, lam.N - 1
+    jac = lam.jacobian(free)[:nn * M * P].reshape(nn, M, P)
+    con = lam.constraints(free)[:M * nn].reshape(M, nn)
+    rng = np.random.default_rng(0)
+    entries = [(int(rng.integers(nn)), int(rng.integers(M)),
+                int(rng.integers(P))) for _ in range(24)]
+    got = lam.jacobian_entries(free, entries)
+    exact = lam.jacobian_entries(free, entries, dps=40)
+    ref = np.array([jac[e] for e in entries])
+    scale = np.array([np.abs(jac[e[0], e[1]]).max() for e in entries])
+    assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref) + 1e-14 * scale)
+    assert np.all(np.abs(exact - ref) <= 1e-10 * np.abs(ref) + 1e-14 * scale)
+    for (node, row, col), v in zip(entries, ref):
+        assert (v != 0.0) == lam.structural_nonzero(row, col) or v == 0.0
+    res = lam.residual_entries(free, [(e[0], e[1]) for e in entries], dps=40)
+    rref = np.array([con[e[1], e[0]] for e in entries])
+    assert np.all(np.abs(res - rref) <= 1e-10 * np.abs(rref) +
+                  1e-14 * np.abs(con).max())

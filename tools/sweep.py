@@ -55,8 +55,6 @@ def main():
         if free is None:
             free = w.free(col.num_free)
         h.upload_free(free)
-        if hasattr(col._evaluator, '_maybe_tune'):
-            col._evaluator._maybe_tune()     # persistent kernel: measured schedule
         h.time_device_evals(20)
         ms = [h.time_device_evals(200) / 200 for _ in range(3)]
         jac = np.array(col.generate_jacobian_function()(free))
