@@ -333,27 +333,57 @@ def run_own_arm(args, rank, world, local_rank):
     value = world * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public API ----------------------------------
-    for i in range(max(args.warmup, 3)):
-        con_f(frees[i % 2])
-        jac_f(frees[i % 2])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        con = con_f(frees[i % 2])
-        jac = jac_f(frees[i % 2])
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    # N = 1: this process' collocator.  N > 1: ONE process (rank 0) drives all
+    # N GPUs through ``devices=`` and receives the whole problem's residual
+    # and Jacobian vectors in one pinned host buffer each -- what a host-side
+    # IPOPT consumes; the other ranks wait.
+    h2d_rows = col.num_states + col.num_unknown_input_trajectories
+    ranges = getattr(ev, 'd2h_ranges', [(0, prog.K)])
+    if world == 1:
+        for i in range(max(args.warmup, 3)):
+            con_f(frees[i % 2])
+            jac_f(frees[i % 2])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            con = con_f(frees[i % 2])
+            jac = jac_f(frees[i % 2])
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        assert con.shape == (prog.M * nn,) and jac.shape == (nn * prog.K,)
+        e2e_how = 'Problem-level callables of this process, host arrays'
+    else:
+        barrier()
+        e2e_s = 0.0
+        if rank == 0:
+            col_all = ConstraintCollocator(
+                *w.collocator_args(), **w.collocator_kwargs(),
+                devices=list(range(world)), cuda_options={'out_ring': 2})
+            con_a = col_all.generate_constraint_function()
+            jac_a = col_all.generate_jacobian_function()
+            for i in range(max(args.warmup, 3)):
+                con_a(frees[i % 2])
+                jac_a(frees[i % 2])
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                con = con_a(frees[i % 2])
+                jac = jac_a(frees[i % 2])
+            e2e_s = time.perf_counter() - t0
+            assert con.shape == (prog.M * nn * world,)
+            assert jac.shape == (nn * world * prog.K,)
+            col_all.close()
+        barrier()
+        e2e_how = ('rank 0 drives all {} GPUs (devices=), full residual and '
+                   'Jacobian vectors assembled in one pinned host buffer '
+                   'each'.format(world))
     if dist is not None:
         t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * args.steps / e2e_s
-    h2d = 8 * ((col.num_states + col.num_unknown_input_trajectories) *
-               (nn + 1) + col.num_unknown_parameters +
+    h2d = 8 * (h2d_rows * (nn * world + 1) + col.num_unknown_parameters +
                int(col._variable_duration))
-    ranges = getattr(ev, 'd2h_ranges', [(0, prog.K)])
-    d2h = 8 * (prog.M * nn + nn * sum(e - b for b, e in ranges))
-    assert con.shape == (prog.M * nn,) and jac.shape == (nn * prog.K,)
+    d2h = 8 * world * (prog.M * nn + nn * sum(e - b for b, e in ranges))
 
     clocks = sampler.stop() if sampler is not None else None
 
@@ -365,12 +395,17 @@ def run_own_arm(args, rank, world, local_rank):
             int(col._variable_duration), prog.M, prog.P, nn + 1, nn)
         launch_ms = ms / args.steps
         achieved = bytes_launch / (launch_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM traffic per launch: from an ncu --set full capture of a launch
+        # INSIDE the rotating-output loop (profiles/roofline_traffic.json says
+        # which); an offline capture, not measured in this run
+        traffic = traffic_note = None
         tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
         if os.path.exists(tpath):
             try:
                 with open(tpath) as f:
-                    traffic = json.load(f).get('dram_bytes_per_launch')
+                    tj = json.load(f)
+                traffic = tj.get('dram_bytes_per_launch')
+                traffic_note = tj.get('source')
             except (OSError, ValueError):
                 traffic = None
         line = {
@@ -381,6 +416,9 @@ def run_own_arm(args, rank, world, local_rank):
             'data': 'synthetic',
             'config': {
                 'workload': WORKLOAD,
+                'value_is': 'device-resident evaluations (free vector and '
+                            'results stay in HBM); the solver-visible rate '
+                            'is e2e',
                 'nodes_per_gpu': nn, 'parallelism': 'node-shard x{}'.format(
                     world),
                 'groups': ev.meta['num_groups'],
@@ -404,6 +442,7 @@ def run_own_arm(args, rank, world, local_rank):
             'roofline': {
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                'traffic_source': traffic_note,
                 'peak_kind': peak_kind,
                 'algorithmic_bytes_per_launch': bytes_launch,
                 'kernel': 'opty_colloc_eval',
@@ -412,7 +451,8 @@ def run_own_arm(args, rank, world, local_rank):
             },
             'e2e': {'value': e2e_value, 'unit': UNIT,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': 1e3 * e2e_s / args.steps},
+                    'ms_per_step': 1e3 * e2e_s / args.steps,
+                    'how': e2e_how},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }

@@ -498,7 +498,8 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
                 min_blocks_per_sm=4, tma_load=True, tma_store=True,
                 derived=(), debug_nostore=False, tile_bufs=2,
                 only_groups=None, with_aux=True, pair=None,
-                schedule_options=None, workers=1):
+                schedule_options=None, workers=1, persistent=False,
+                num_sms=148):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block,
     whole equations each; a group also owns the residuals of its rows).
@@ -558,6 +559,10 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     w('#define OPTY_TMA_LOAD {}'.format(int(tma_load)))
     w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
     w('#define OPTY_NBUF {}'.format(tile_bufs))
+    if persistent:
+        w('#define OPTY_PERSISTENT 1')
+        w('#define OPTY_SM_TABLE {}'.format(num_sms))
+    w('#define OPTY_PRE_GROUPS {}'.format(len(set(T.a[nid] for nid in derived))))
     if debug_nostore:
         w('#define OPTY_DEBUG_NOSTORE {}'.format(int(debug_nostore)))
     w('#include "colloc_kernel.cuh"')
@@ -645,6 +650,26 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
                                    43 * group_meta[g]['ncols']))
     w('__device__ const int opty_group_order[OPTY_NGROUPS] = {{{}}};'.format(
         ', '.join(str(g) for g in order)))
+    if persistent:
+        # slot = position in opty_group_order.  SMs are dealt out to the
+        # slots in proportion to the slots' cost; every block of an SM starts
+        # on the SM's slot
+        costs = [20 * group_meta[g]['ops'] + 43 * group_meta[g]['ncols']
+                 for g in order]
+        total = float(sum(costs)) or 1.0
+        table = []
+        acc = 0.0
+        slot = 0
+        for sm in range(num_sms):
+            target = (sm + 0.5) / num_sms * total
+            while slot < len(costs) - 1 and acc + costs[slot] < target:
+                acc += costs[slot]
+                slot += 1
+            table.append(slot)
+        w('__device__ const int opty_sm_group[OPTY_SM_TABLE] = {{{}}};'.format(
+            ', '.join(str(v) for v in table)))
+        w('__device__ const int opty_slot_cost[OPTY_NGROUPS] = {{{}}};'.format(
+            ', '.join(str(max(1, int(c // 100))) for c in costs)))
     w('')
     info = [0] * INFO_WORDS
     info[0] = INFO_MAGIC
@@ -665,6 +690,8 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     info[21] = M
     info[22] = P
     info[23] = 1 if with_aux else 0
+    info[24] = 1 if persistent else 0
+    info[25] = min_blocks_per_sm
     w('extern "C" __device__ const int opty_module_info[{}] = {{{}}};'.format(
         INFO_WORDS, ', '.join(str(v) for v in info)))
     w('')
@@ -701,6 +728,7 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         'tma_load': int(tma_load),
         'tma_store': bool(tma_store),
         'tile_bufs': tile_bufs,
+        'persistent': bool(persistent),
         'method': method,
         'schedule': opts,
         'entry_kind': prog.entry_kind(),

@@ -56,6 +56,7 @@
 #define OPTY_XSEG 128
 #endif
 #define OPTY_XBOX (OPTY_XSEG + 2)
+#define OPTY_TW (OPTY_THREADS + 2)  // row pitch of the tiled trajectory layout (direct input loads)
 #define OPTY_NSEG (OPTY_THREADS / OPTY_XSEG)
 #define OPTY_XSEG_BYTES (((OPTY_RD * OPTY_XBOX * 8) + 127) / 128 * 128)
 #ifndef OPTY_NBUF
@@ -146,16 +147,22 @@ static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map,
 // read again (schedule.py); a compiler that merged the loads would pin the
 // register for the whole distance between them.
 #if OPTY_TMA_LOAD == 2
-// direct mode: no staging; lanes read consecutive columns of a row (coalesced,
-// read-only path), the neighbour column comes from the same cache lines
+// direct mode: no shared-memory staging; the pre-pass kernel lays the
+// trajectory matrix and the derived rows out tile by tile
+// ([tiles][R + D][OPTY_TW], OPTY_TW = nodes of a block + 2), so that every row
+// of a block's slice sits at a compile-time offset from one base pointer: a
+// load is `ld.global.nc [base + immediate]`, lanes read consecutive columns
+// (coalesced), the neighbour column comes from the same cache lines.  (With a
+// run-time row pitch every row needs its own 64-bit address register; ptxas
+// keeps hundreds of them alive in large bodies and spills.)
 static __device__ __forceinline__ double opty_ldin(const double* p) {
   double v;
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
-#define XA(r) opty_ldin(ctx.xg + (long long)(r) * ctx.ldt)
-#define XB(r) opty_ldin(ctx.xg + (long long)(r) * ctx.ldt + 1)
-#define XD(d) opty_ldin(ctx.xg + (long long)(OPTY_R + (d)) * ctx.ldt)
+#define XA(r) opty_ldin(ctx.xg + (r) * OPTY_TW)
+#define XB(r) opty_ldin(ctx.xg + (r) * OPTY_TW + 1)
+#define XD(d) opty_ldin(ctx.xg + (OPTY_R + (d)) * OPTY_TW)
 #else
 static __device__ __forceinline__ double opty_ldin(uint32_t a) {
   double v;
@@ -237,19 +244,24 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
 #endif
 #define OPTY_SMEM_BYTES (OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES + 128)
 
+// stages the slice of node tile `tile_node0` (mbarrier parity `xphase`)
 #if OPTY_TMA_LOAD == 2
+#define OPTY_STAGE_INIT()
 #define OPTY_STAGE_INPUT()
 #elif OPTY_TMA_LOAD == 1
+#define OPTY_STAGE_INIT()                     \
+  if (threadIdx.x == 0) opty_mbar_init(bar, 1); \
+  __syncthreads();
 #define OPTY_STAGE_INPUT()                                                                               \
   if (threadIdx.x == 0) {                                                                                \
-    opty_mbar_init(bar, 1);                                                                              \
     opty_mbar_expect_tx(bar, OPTY_NSEG * OPTY_RD * OPTY_XBOX * 8);                                       \
     for (int sgm = 0; sgm < OPTY_NSEG; ++sgm)                                                            \
       opty_tma_load_2d(xin_bytes + sgm * OPTY_XSEG_BYTES, &tm.in, tile_node0 + sgm * OPTY_XSEG, 0, bar); \
   }                                                                                                      \
-  __syncthreads();                                                                                       \
-  opty_mbar_wait(bar, 0);
+  opty_mbar_wait(bar, xphase);                                                                           \
+  xphase ^= 1u;
 #else
+#define OPTY_STAGE_INIT()
 #define OPTY_STAGE_INPUT()                                                                               \
   for (int sgm = 0; sgm < OPTY_NSEG; ++sgm) {                                                            \
     double* dstseg = reinterpret_cast<double*>(xin_bytes + sgm * OPTY_XSEG_BYTES);                       \
@@ -262,53 +274,177 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
   __syncthreads();
 #endif
 
-// One block = one tile of 32*W nodes x one output group; grid = (tiles, groups).
-// blockIdx.y walks the groups in the order the emitter chose (most expensive
-// first, so that the cheap groups fill the tail of the launch); the hardware
-// block scheduler balances the SMs.
-//
-// The generated kernel body sits between OPTY_KERNEL_BEGIN and OPTY_KERNEL_END
-// and dispatches on `opty_g`.
-#define OPTY_KERNEL_BEGIN()                                                                              \
-  extern __shared__ __align__(128) unsigned char opty_smem[];                                            \
-  double* tiles = reinterpret_cast<double*>(opty_smem);                                                  \
-  unsigned char* xin_bytes = opty_smem + OPTY_SMEM_TILES_BYTES;                                          \
-  uint64_t* bar = reinterpret_cast<uint64_t*>(opty_smem + OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES);  \
-  (void)bar;                                                                                             \
-  (void)xin_bytes;                                                                                       \
-  const int opty_g = opty_group_order[blockIdx.y];                                                       \
-  const int tile_node0 = blockIdx.x * OPTY_THREADS;                                                      \
-  OPTY_STAGE_INPUT()                                                                                     \
-  OptyCtx ctx;                                                                                           \
-  ctx.lane = threadIdx.x & 31;                                                                           \
-  ctx.n_nodes = p.n_nodes;                                                                               \
-  ctx.ldt = p.ldt;                                                                                       \
-  OPTY_CTX_INPUT()                                                                                       \
-  ctx.ldc = p.ldc;                                                                                       \
-  ctx.tile0 = tiles + (threadIdx.x >> 5) * OPTY_NBUF * OPTY_TILE_DOUBLES;                                \
-  ctx.jac = p.jac;                                                                                       \
-  ctx.tm = &tm;                                                                                          \
-  ctx.node = tile_node0 + (threadIdx.x & ~31);                                                           \
-  ctx.active = (tile_node0 + (int)threadIdx.x) < p.n_nodes;                                              \
-  ctx.con = p.con + tile_node0 + threadIdx.x;                                                            \
-  if (ctx.node >= p.n_nodes) return;
-
 #if OPTY_TMA_LOAD == 2
-#define OPTY_CTX_INPUT() ctx.xg = p.traj + min(tile_node0 + (int)threadIdx.x, p.n_nodes - 1);
+#define OPTY_CTX_INPUT() \
+  ctx.xg = p.tiled + (long long)(tile_node0 / OPTY_THREADS) * (OPTY_RD * OPTY_TW) + threadIdx.x;
 #else
 #define OPTY_CTX_INPUT()                                                                \
   ctx.xs = opty_smem_u32(xin_bytes + (threadIdx.x / OPTY_XSEG) * OPTY_XSEG_BYTES) +    \
            (threadIdx.x % OPTY_XSEG) * 8;
 #endif
 
+#define OPTY_SMEM_SETUP()                                                                                \
+  extern __shared__ __align__(128) unsigned char opty_smem[];                                            \
+  double* tiles = reinterpret_cast<double*>(opty_smem);                                                  \
+  unsigned char* xin_bytes = opty_smem + OPTY_SMEM_TILES_BYTES;                                          \
+  uint64_t* bar = reinterpret_cast<uint64_t*>(opty_smem + OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES);  \
+  uint32_t xphase = 0;                                                                                   \
+  (void)bar;                                                                                             \
+  (void)xin_bytes;                                                                                       \
+  (void)xphase;
+
+#define OPTY_CTX_SETUP()                                                  \
+  OptyCtx ctx;                                                            \
+  ctx.lane = threadIdx.x & 31;                                            \
+  ctx.n_nodes = p.n_nodes;                                                \
+  ctx.ldt = p.ldt;                                                        \
+  OPTY_CTX_INPUT()                                                        \
+  ctx.ldc = p.ldc;                                                        \
+  ctx.tile0 = tiles + (threadIdx.x >> 5) * OPTY_NBUF * OPTY_TILE_DOUBLES; \
+  ctx.jac = p.jac;                                                        \
+  ctx.tm = &tm;                                                           \
+  ctx.node = tile_node0 + (threadIdx.x & ~31);                            \
+  ctx.active = (tile_node0 + (int)threadIdx.x) < p.n_nodes;               \
+  ctx.con = p.con + tile_node0 + threadIdx.x;
+
+#ifndef OPTY_PERSISTENT
+#define OPTY_PERSISTENT 0
+#endif
+
+#if !OPTY_PERSISTENT
+// Grid kernel: one block = one tile of 32*W nodes x one output group; grid =
+// (tiles, groups).  blockIdx.y walks the groups in the order the emitter chose
+// (most expensive first, so that the cheap groups fill the tail of the
+// launch); the hardware block scheduler balances the SMs.
+//
+// The generated kernel body sits between OPTY_KERNEL_BEGIN and OPTY_KERNEL_END
+// and dispatches on `opty_g`.
+#define OPTY_KERNEL_BEGIN()                          \
+  OPTY_SMEM_SETUP()                                  \
+  const int opty_g = opty_group_order[blockIdx.y];   \
+  const int tile_node0 = blockIdx.x * OPTY_THREADS;  \
+  OPTY_STAGE_INIT()                                  \
+  OPTY_STAGE_INPUT()                                 \
+  OPTY_CTX_SETUP()                                   \
+  if (ctx.node >= p.n_nodes) return;
+
 #define OPTY_KERNEL_END()
+
+#else
+// Persistent, code-stationary kernel: grid = (resident blocks per SM) x SMs.
+// Every warp of the generated code walks its straight-line body exactly once
+// per node tile, so a block that changes its group with every tile streams
+// its instructions through the GPC-level cache and stalls on instruction
+// fetch for more than half of its cycles (profiles/).  Here a block keeps ONE
+// group for as long as that group has tiles left -- the body stays in the SM's
+// instruction cache -- and all blocks of an SM start on the same group
+// (`opty_sm_group`, indexed by %smid: SMs are dealt out to the groups in
+// proportion to their cost).  Tiles are handed out by one atomic counter per
+// group (`p.work`), asked for one tile ahead so that the round trip hides
+// behind the arithmetic; a block whose group has run dry moves to the group
+// with the most work left, which balances the load without a cost model that
+// has to be right.  The last block to leave resets the counters for the next
+// launch.
+// next (slot, tile) for a block whose current slot has run dry: the slot with
+// the most work left (one look at all counters, then one atomic)
+static __device__ __noinline__ int2 opty_steal(const OptyParams& p, const int* opty_slot_cost) {
+  for (int tries = 0; tries < OPTY_NGROUPS; ++tries) {
+    int best = -1;
+    long long best_left = 0;
+    for (int s_ = 0; s_ < OPTY_NGROUPS; ++s_) {
+      const int done = *reinterpret_cast<volatile int*>(p.work + s_);
+      const long long left = (long long)(p.n_tiles - done) * opty_slot_cost[s_];
+      if (left > best_left) {
+        best_left = left;
+        best = s_;
+      }
+    }
+    if (best < 0) break;
+    const int t_ = atomicAdd(p.work + best, 1);
+    if (t_ < p.n_tiles) return make_int2(best, t_);
+  }
+  return make_int2(-1, 0);
+}
+
+#define OPTY_KERNEL_BEGIN()                                                                            \
+  OPTY_SMEM_SETUP()                                                                                    \
+  __shared__ int opty_next[2];                                                                         \
+  OPTY_STAGE_INIT()                                                                                    \
+  unsigned opty_smid;                                                                                  \
+  asm("mov.u32 %0, %%smid;" : "=r"(opty_smid));                                                        \
+  if (threadIdx.x == 0) {                                                                              \
+    const int s0_ = opty_sm_group[opty_smid % OPTY_SM_TABLE];                                          \
+    int t0_ = atomicAdd(p.work + s0_, 1);                                                              \
+    int2 a_ = t0_ < p.n_tiles ? make_int2(s0_, t0_) : opty_steal(p, opty_slot_cost);                                   \
+    opty_next[0] = a_.x;                                                                               \
+    opty_next[1] = a_.y;                                                                               \
+  }                                                                                                    \
+  __syncthreads();                                                                                     \
+  int opty_slot = opty_next[0], opty_t = opty_next[1];                                                 \
+  while (opty_slot >= 0) {                                                                             \
+    __syncthreads(); /* everybody has read opty_next and is done with the previous input slice */      \
+    /* the next tile of this slot is asked for now and looked at after the body */                     \
+    int opty_raw = 0;                                                                                  \
+    if (threadIdx.x == 0) opty_raw = atomicAdd(p.work + opty_slot, 1);                                 \
+    const int opty_g = opty_group_order[opty_slot];                                                    \
+    const int tile_node0 = opty_t * OPTY_THREADS;                                                      \
+    OPTY_STAGE_INPUT()                                                                                 \
+    OPTY_CTX_SETUP()                                                                                   \
+    if (ctx.node < p.n_nodes) {
+
+#define OPTY_KERNEL_END()                                                                              \
+    }                                                                                                  \
+    if (threadIdx.x == 0) {                                                                            \
+      int2 a_ = opty_raw < p.n_tiles ? make_int2(opty_slot, opty_raw) : opty_steal(p, opty_slot_cost);                 \
+      opty_next[0] = a_.x;                                                                             \
+      opty_next[1] = a_.y;                                                                             \
+    }                                                                                                  \
+    __syncthreads();                                                                                   \
+    opty_slot = opty_next[0];                                                                          \
+    opty_t = opty_next[1];                                                                             \
+  }                                                                                                    \
+  if (threadIdx.x == 0) {                                                                              \
+    __threadfence();                                                                                   \
+    if (atomicInc(reinterpret_cast<unsigned*>(p.work + OPTY_NGROUPS), gridDim.x - 1) == gridDim.x - 1) \
+      for (int g_ = 0; g_ < OPTY_NGROUPS; ++g_) p.work[g_] = 0;                                        \
+  }
+#endif
 
 // ---------------------------------------------------------------------------
 // pre-pass kernel: one thread per node, derived rows written coalesced
 // ---------------------------------------------------------------------------
+// With direct input loads (OPTY_TMA_LOAD == 2) the derived rows go to the
+// tiled layout, and blockIdx.y >= OPTY_PRE_GROUPS copies chunks of
+// OPTY_COPY_ROWS trajectory rows there: thread = column, its value goes to its
+// own tile and, for the first two columns of a tile, also to the halo slots of
+// the tile before.
 #define OPTY_PRE_THREADS 128
+#define OPTY_COPY_ROWS 16
 #define GA(r) __ldcg(xg + (long long)(r) * p.ldt)
 #define GB(r) __ldcg(xg + (long long)(r) * p.ldt + 1)
+#if OPTY_TMA_LOAD == 2
+#define OPTY_DRV(d, val) drv[(d) * OPTY_TW] = (val)
+#define OPTY_PRE_BEGIN()                                                                              \
+  const int node = blockIdx.x * OPTY_PRE_THREADS + threadIdx.x;                                       \
+  const int opty_pg = blockIdx.y;                                                                     \
+  if (opty_pg >= OPTY_PRE_GROUPS) {                                                                   \
+    if (node < p.n_cols) {                                                                            \
+      const int t_ = node / OPTY_THREADS, j_ = node % OPTY_THREADS;                                   \
+      const int r0_ = (opty_pg - OPTY_PRE_GROUPS) * OPTY_COPY_ROWS;                                   \
+      double* own_ = p.tiled + (long long)t_ * (OPTY_RD * OPTY_TW) + j_;                              \
+      for (int r_ = r0_; r_ < min(r0_ + OPTY_COPY_ROWS, OPTY_R); ++r_) {                              \
+        const double v_ = __ldcg(p.traj + (long long)r_ * p.ldt + node);                              \
+        own_[r_ * OPTY_TW] = v_;                                                                      \
+        if (j_ < 2 && t_ > 0) own_[r_ * OPTY_TW - (OPTY_RD * OPTY_TW) + OPTY_THREADS] = v_;           \
+      }                                                                                               \
+    }                                                                                                 \
+    return;                                                                                           \
+  }                                                                                                   \
+  if (node >= p.n_nodes) return;                                                                      \
+  const double* xg = p.traj + node;                                                                   \
+  double* drv = p.tiled + (long long)(node / OPTY_THREADS) * (OPTY_RD * OPTY_TW) +                    \
+                (long long)OPTY_R * OPTY_TW + node % OPTY_THREADS;
+#else
 #define OPTY_DRV(d, val) drv[(long long)(d) * p.ldt] = (val)
 #define OPTY_PRE_BEGIN()                                        \
   const int node = blockIdx.x * OPTY_PRE_THREADS + threadIdx.x; \
@@ -316,3 +452,4 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
   const double* xg = p.traj + node;                             \
   double* drv = p.traj + (long long)OPTY_R * p.ldt + node;      \
   const int opty_pg = blockIdx.y;
+#endif

@@ -4,10 +4,15 @@
 
 struct OptyParams {
   double* traj;   // [R + D][ldt] trajectory matrix + derived rows
+  double* tiled;  // direct-input modules: the same values tile by tile, [tiles][R + D][32*W + 2]: node tile,
+                  // row, node inside the tile plus the two columns that follow it -- every row of a block's
+                  // slice at a compile-time offset from one base pointer
   double* con;    // [M][ldc] residuals, eom-major
   double* jac;    // [nodes][K] partials, node-major
   long long ldt;
   long long ldc;
   int n_nodes;    // constraint nodes in this launch (N - 1 or a shard of them)
   int n_cols;     // valid trajectory columns (n_nodes + 1)
+  int n_tiles;    // node tiles of 32*W nodes (persistent kernel)
+  int* work;      // persistent kernel: next tile per group [groups of the module] + departure counter
 };

@@ -65,6 +65,7 @@ struct DriverApi {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                            unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
   CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -96,6 +97,8 @@ int init_driver() {
   if ((rc = load_entry("cuFuncSetAttribute", &g_drv.FuncSetAttribute))) return rc;
   if ((rc = load_entry("cuLaunchKernel", &g_drv.LaunchKernel))) return rc;
   if ((rc = load_entry("cuGetErrorString", &g_drv.GetErrorString))) return rc;
+  if ((rc = load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", &g_drv.OccupancyMaxActiveBlocksPerMultiprocessor)))
+    return rc;
   if ((rc = load_entry("cuTensorMapEncodeTiled", &g_drv.TensorMapEncodeTiled))) return rc;
   g_drv.ready = true;
   return OPTY_OK;
@@ -233,6 +236,7 @@ enum {
   INFO_M = 21,
   INFO_P = 22,
   INFO_HAS_AUX = 23,
+  INFO_PERSISTENT = 24,
   INFO_WORDS = 32
 };
 const int kInfoMagic = 0x4f505459;
@@ -254,7 +258,7 @@ struct opty_colloc {
 
   // kernel geometry, read from the primary module
   int warps = 0, num_derived = 0, pre_groups = 0, tma_load = 0, tma_store = 0, tile_bufs = 0,
-      tile_doubles = 0, num_inv = 0;
+      tile_doubles = 0, num_inv = 0, persistent = 0;
 
   struct Module {
     CUmodule mod = nullptr;
@@ -264,6 +268,8 @@ struct opty_colloc {
     int nmaps = 0;
     int widths[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<std::vector<unsigned char>> tmaps;  // per ring slot: OptyTmaps blob (in + out[nmaps])
+    int* d_work = nullptr;      // persistent kernel: tile counter per group + departure counter
+    unsigned persist_grid = 0;  // resident blocks on the whole device
   };
   std::vector<Module> modules;  // [0] = primary (carries opty_colloc_inv / opty_colloc_pre)
   CUfunction f_inv = nullptr;
@@ -280,6 +286,7 @@ struct opty_colloc {
   uint64_t copy_seq = 0;                // evaluation the most recent speculative copy belongs to
 
   double* d_traj = nullptr;
+  double* d_tiled = nullptr;  // direct-input modules: trajectory + derived rows tile by tile (colloc_params.h)
   double* d_uni = nullptr;
   double* d_inv = nullptr;
   std::vector<double*> d_con, d_jac;
@@ -389,13 +396,14 @@ int load_module(opty_colloc* h, const void* cubin, bool primary) {
     h->tile_bufs = info[INFO_TILE_BUFS];
     h->tile_doubles = info[INFO_TILE_DOUBLES];
     h->num_inv = info[INFO_NUM_INV];
+    h->persistent = info[INFO_PERSISTENT];
     if (h->warps < 1 || h->warps > 32 || h->tile_bufs < 1 || h->tile_bufs > 2 || h->tile_doubles < 64 ||
         h->num_derived < 0 || (h->num_derived > 0 && h->pre_groups < 1))
       return bail(fail(OPTY_ERR_ARG, "invalid kernel geometry in the module info table"));
   } else if (info[INFO_WARPS] != h->warps || info[INFO_DERIVED] != h->num_derived ||
              info[INFO_TMA_LOAD] != h->tma_load || info[INFO_TMA_STORE] != h->tma_store ||
              info[INFO_TILE_BUFS] != h->tile_bufs || info[INFO_TILE_DOUBLES] != h->tile_doubles ||
-             info[INFO_NUM_INV] != h->num_inv) {
+             info[INFO_NUM_INV] != h->num_inv || info[INFO_PERSISTENT] != h->persistent) {
     return bail(fail(OPTY_ERR_ARG, "additional module does not match the geometry of the first one"));
   }
   m.num_groups = info[INFO_GROUPS];
@@ -427,6 +435,15 @@ int finish_module(opty_colloc* h, opty_colloc::Module& m) {
   for (int s = 0; s < h->cfg.out_ring; ++s) {
     int rc = build_tmaps(h, m, s);
     if (rc) return rc;
+  }
+  if (h->persistent) {
+    // as many blocks as fit on the device at once: every block loops over node tiles
+    int per_sm = 0;
+    DRV_CHECK(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m.f_eval, 32 * h->warps, h->smem_bytes));
+    if (per_sm < 1) return fail(OPTY_ERR_ARG, "the persistent kernel does not fit on an SM");
+    m.persist_grid = (unsigned)per_sm * (unsigned)h->num_sms;
+    RT_CHECK(cudaMalloc(&m.d_work, (size_t)(m.num_groups + 1) * sizeof(int)));
+    RT_CHECK(cudaMemset(m.d_work, 0, (size_t)(m.num_groups + 1) * sizeof(int)));
   }
   return OPTY_OK;
 }
@@ -464,22 +481,38 @@ int launch_eval(opty_colloc* h, bool record_events = false) {
   h->eval_seq++;
   OptyParams p;
   p.traj = h->d_traj;
+  p.tiled = h->d_tiled;
   p.con = h->d_con[h->ring];
   p.jac = h->d_jac[h->ring];
   p.ldt = h->ldt;
   p.ldc = h->nn;
   p.n_nodes = h->nn;
   p.n_cols = h->ncols;
-  if (h->num_derived > 0) {
-    void* pargs[1] = {&p};
-    DRV_CHECK(g_drv.LaunchKernel(h->f_pre, (unsigned)((h->nn + 127) / 128), (unsigned)h->pre_groups, 1, 128, 1, 1, 0,
-                                 (CUstream)h->stream, pargs, nullptr));
-    h->launches++;
+  p.n_tiles = (int)h->grid_x;
+  p.work = nullptr;
+  {
+    // pre-pass: derived rows, and for direct-input modules the tile-by-tile copy of the trajectory rows
+    // (chunks of 16 rows in grid.y behind the groups of derived rows)
+    const unsigned copy_groups = h->tma_load == 2 ? (unsigned)((h->R + 15) / 16) : 0u;
+    const unsigned gy = (h->num_derived > 0 ? (unsigned)h->pre_groups : 0u) + copy_groups;
+    if (gy > 0) {
+      void* pargs[1] = {&p};
+      DRV_CHECK(g_drv.LaunchKernel(h->f_pre, (unsigned)((h->nn + 1 + 127) / 128), gy, 1, 128, 1, 1, 0,
+                                   (CUstream)h->stream, pargs, nullptr));
+      h->launches++;
+    }
   }
   for (auto& m : h->modules) {
+    p.work = m.d_work;
     void* args[2] = {m.tmaps[h->ring].data(), &p};
-    DRV_CHECK(g_drv.LaunchKernel(m.f_eval, h->grid_x, (unsigned)m.num_groups, 1, 32u * h->warps, 1, 1,
-                                 h->smem_bytes, (CUstream)h->stream, args, nullptr));
+    if (h->persistent) {
+      // code-stationary persistent kernel: resident blocks pull (group, tile) work items
+      DRV_CHECK(g_drv.LaunchKernel(m.f_eval, m.persist_grid, 1, 1, 32u * h->warps, 1, 1, h->smem_bytes,
+                                   (CUstream)h->stream, args, nullptr));
+    } else {
+      DRV_CHECK(g_drv.LaunchKernel(m.f_eval, h->grid_x, (unsigned)m.num_groups, 1, 32u * h->warps, 1, 1,
+                                   h->smem_bytes, (CUstream)h->stream, args, nullptr));
+    }
     h->launches++;
   }
   if (record_events) {
@@ -722,6 +755,11 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   CREATE_CHECK(finish_module(h, h->modules[0]));
 
   h->grid_x = (unsigned)((h->nn + 32 * h->warps - 1) / (32 * h->warps));
+  if (h->tma_load == 2) {
+    const size_t tiled_bytes = (size_t)h->grid_x * h->RD * (32 * h->warps + 2) * 8;
+    CREATE_RT(cudaMalloc(&h->d_tiled, tiled_bytes));
+    CREATE_RT(cudaMemsetAsync(h->d_tiled, 0, tiled_bytes, h->stream));
+  }
   CREATE_RT(cudaStreamSynchronize(h->stream));
   *out = h;
   return OPTY_OK;
@@ -735,6 +773,7 @@ int opty_colloc_destroy(opty_colloc_t* h) {
   for (double* p : h->d_con) cudaFree(p);
   for (double* p : h->d_jac) cudaFree(p);
   cudaFree(h->d_traj);
+  cudaFree(h->d_tiled);
   cudaFree(h->d_uni);
   cudaFree(h->d_inv);
   cudaFree(h->d_quad_partial);
@@ -751,8 +790,10 @@ int opty_colloc_destroy(opty_colloc_t* h) {
   if (h->ev_con) cudaEventDestroy(h->ev_con);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
-  for (auto& m : h->modules)
+  for (auto& m : h->modules) {
+    cudaFree(m.d_work);
     if (m.mod && g_drv.ModuleUnload) g_drv.ModuleUnload(m.mod);
+  }
   delete h;
   return OPTY_OK;
 }

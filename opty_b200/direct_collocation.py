@@ -64,6 +64,11 @@ DEFAULT_CUDA_OPTIONS = {
                                 # shared memory, False = plain loads into
                                 # shared memory, 'direct' = no staging
     'tma_store': True,
+    'persistent': False,        # code-stationary persistent main kernel: the
+                                # resident blocks of an SM keep one group for
+                                # as long as it has node tiles left (the body
+                                # stays in the instruction cache) and pull
+                                # tiles from per-group atomic counters
     'pre_pass': True,           # shared expensive sub-expressions once per node
     'schedule': True,           # register-pressure scheduler (schedule.py);
                                 # False: outputs in column order, temporaries
@@ -115,8 +120,14 @@ class ConstraintCollocator(object):
     ----------------------------
     backend : 'cuda'
     device : int, CUDA device ordinal (default ``LOCAL_RANK`` or 0)
+    devices : sequence of CUDA device ordinals.  The constraint nodes are
+        split into one contiguous shard per device, all driven by this one
+        process; every shard copies its residuals and Jacobian block straight
+        into its slice of ONE pinned host vector, so that ``constraints`` /
+        ``jacobian`` return the whole problem's vectors like a single-device
+        collocator does.
     node_range : (lo, hi), evaluate only constraint nodes ``lo <= i < hi`` of
-        the ``N - 1`` (used for sharding the nodes over several GPUs)
+        the ``N - 1`` (used for sharding the nodes over several processes)
     cuda_options : dict overriding ``DEFAULT_CUDA_OPTIONS``
     """
 
@@ -126,7 +137,7 @@ class ConstraintCollocator(object):
                  instance_constraints=None, time_symbol=None, tmp_dir=None,
                  integration_method='backward euler', parallel=False,
                  show_compile_output=False, backend='cuda', device=None,
-                 node_range=None, cuda_options=None):
+                 node_range=None, cuda_options=None, devices=None):
         self._eom = equations_of_motion
 
         # the reference also redirects the global default time symbol
@@ -176,6 +187,17 @@ class ConstraintCollocator(object):
                     sorted(unknown)))
             opts.update(cuda_options)
         self._cuda_options = opts
+        self._devices = None
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            if not devices or len(set(devices)) != len(devices):
+                raise ValueError('devices must be a non-empty sequence of '
+                                 'distinct CUDA device ordinals.')
+            if device is not None and int(device) != devices[0]:
+                raise ValueError('Give either device or devices.')
+            device = devices[0]
+            if len(devices) > 1:
+                self._devices = devices
         if device is None:
             device = int(os.environ.get('LOCAL_RANK', 0))
         self._device = int(device)
@@ -276,6 +298,7 @@ class ConstraintCollocator(object):
     tmp_dir = property(lambda self: self._tmp_dir)
     node_range = property(lambda self: self._node_range)
     device = property(lambda self: self._device)
+    devices = property(lambda self: self._devices or [self._device])
 
     @integration_method.setter
     def integration_method(self, method):
@@ -544,7 +567,10 @@ class ConstraintCollocator(object):
 
     def _build_evaluator(self):
         if self._evaluator is None:
-            self._evaluator = _CudaEvaluator(self)
+            if self._devices:
+                self._evaluator = _MultiDeviceEvaluator(self, self._devices)
+            else:
+                self._evaluator = _CudaEvaluator(self)
         return self._evaluator
 
     def close(self):
@@ -665,6 +691,7 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         tile_cols=tile_cols, warps_per_block=wpb, min_blocks_per_sm=mbs,
         tma_load=tma_load, tma_store=tma_store, derived=derived,
         debug_nostore=opts['debug_nostore'], tile_bufs=tile_bufs, pair=pair,
+        persistent=bool(opts['persistent']),
         schedule_options=sched_opts,
         workers=(os.cpu_count() or 1) if cost >= 20000 else 1)
 
@@ -962,7 +989,7 @@ class _CudaEvaluator(object):
             if len(ranges) > 8:
                 ranges = [(ranges[0][0], ranges[-1][1])]
         self.d2h_ranges = ranges
-        self.handle.set_d2h_columns(ranges, None)
+        self.handle.set_d2h_columns(ranges)
 
     # callbacks --------------------------------------------------------
     def _check_free(self, free):
@@ -998,6 +1025,114 @@ class _CudaEvaluator(object):
         self.handle.close()
 
 
+class _MultiDeviceEvaluator(object):
+    """Several GPUs driven by one process: one :class:`_CudaEvaluator` per
+    device, each on a contiguous shard of the constraint nodes.  The shards
+    need no data-path collective (node ``i`` reads trajectory columns ``i``
+    and ``i + 1`` only, opty/direct_collocation.py:2145, 2153-2155): every
+    device receives its window of the free vector and copies its residuals
+    (``M`` strided segments of the eom-major vector, opty/direct_collocation
+    .py:2446) and its Jacobian block (one contiguous slice of the node-major
+    vector, opty/direct_collocation.py:2681-2684) straight into ONE pinned
+    host vector each -- what a host-side IPOPT consumes."""
+
+    def __init__(self, col, devices):
+        import copy
+        from .sharding import node_shard
+        self.col = col
+        lo, hi = col._node_range
+        G = len(devices)
+        if hi - lo < G:
+            raise ValueError('more devices than constraint nodes')
+        self.children = []
+        self.shards = []
+        for g, dev in enumerate(devices):
+            a, b = node_shard(hi - lo + 1, g, G)
+            part = copy.copy(col)
+            part._node_range = (lo + a, lo + b)
+            part._device = dev
+            part._devices = None
+            part._evaluator = None
+            # the whole problem's instance constraints are appended here, not
+            # by a shard
+            self.shards.append(part._node_range)
+            self.children.append(part)
+        M = col.num_eom
+        first = None
+        self.evaluators = []
+        for part in self.children:
+            ev = _CudaEvaluator(part)
+            self.evaluators.append(ev)
+            first = first or ev
+        self.program = first.program
+        self.meta = first.meta
+        P = self.program.P
+        K = M * P
+        N = col.num_collocation_nodes
+        owns = col._owns_instance()
+        self.num_inst = col.num_instance_constraints if owns else 0
+        self.nnz_inst = 0
+        if self.num_inst:
+            self.nnz_inst = len(col._instance_constraints_jacobian_indices()[0])
+        # full-problem host vectors (the shards of a sub-range collocator
+        # still index them by global node)
+        self.con_full = runtime.PinnedArray(M * (N - 1) + self.num_inst)
+        self.jac_full = runtime.PinnedArray((N - 1) * K + self.nnz_inst)
+        for ev in self.evaluators:
+            ev.handle.set_host_outputs(self.con_full, self.jac_full)
+        self.nn = hi - lo
+        self.con_len = M * (N - 1)
+        self.jac_len = (N - 1) * K
+        self._lo, self._hi, self._M, self._K, self._N = lo, hi, M, K, N
+
+    def _check_free(self, free):
+        return self.evaluators[0]._check_free(free)
+
+    def _run(self, free, want_con, want_jac):
+        for ev in self.evaluators:
+            ev._push_known(free)
+        for ev in self.evaluators:
+            ev.handle.begin(free, want_con, want_jac)
+        for ev in self.evaluators:
+            ev.handle.finish()
+
+    def constraints(self, free):
+        free = self._check_free(free)
+        self._run(free, True, False)
+        M, N, lo, hi = self._M, self._N, self._lo, self._hi
+        con = self.con_full.array
+        if (lo, hi) == (0, N - 1):
+            out = con.copy()
+        else:
+            out = np.ascontiguousarray(
+                con[:M * (N - 1)].reshape(M, N - 1)[:, lo:hi]).ravel()
+        if self.num_inst:
+            out[self.con_len:] = self.col.eval_instance_constraints(free)
+        return out
+
+    def jacobian(self, free, refetch=False):
+        free = self._check_free(free)
+        if refetch:
+            for ev in self.evaluators:
+                ev.handle.invalidate_host_jacobian()
+        self._run(free, False, True)
+        jac = self.jac_full.array
+        if self.num_inst:
+            jac[self.jac_len:] = \
+                self.col.eval_instance_constraints_jacobian_values(free)
+        K, lo, hi, N = self._K, self._lo, self._hi, self._N
+        if (lo, hi) == (0, N - 1):
+            return jac
+        return jac[lo * K:hi * K]
+
+    def close(self):
+        for ev in self.evaluators:
+            ev.close()
+        self.evaluators = []
+        self.con_full.close()
+        self.jac_full.close()
+
+
 class Problem(_IpoptBase):
     """NLP facade with the reference's constructor signature
     (opty/direct_collocation.py:139-145) and cyipopt callbacks
@@ -1017,7 +1152,8 @@ class Problem(_IpoptBase):
                  instance_constraints=None, time_symbol=None, tmp_dir=None,
                  integration_method='backward euler', parallel=False,
                  bounds=None, show_compile_output=False, backend='cuda',
-                 eom_bounds=None, device=None, cuda_options=None):
+                 eom_bounds=None, device=None, cuda_options=None,
+                 devices=None):
 
         if not equations_of_motion.has(sm.Derivative):
             raise ValueError('No time derivatives are present. The equations '
@@ -1030,7 +1166,8 @@ class Problem(_IpoptBase):
             node_time_interval, known_parameter_map, known_trajectory_map,
             instance_constraints, time_symbol, tmp_dir, integration_method,
             parallel, show_compile_output=show_compile_output,
-            backend=backend, device=device, cuda_options=cuda_options)
+            backend=backend, device=device, cuda_options=cuda_options,
+            devices=devices)
 
         self._bounds = bounds
         if eom_bounds is not None:
@@ -1077,9 +1214,6 @@ class Problem(_IpoptBase):
         code = func.__code__
         defaults = func.__defaults__
         return code.co_argcount - (len(defaults) if defaults else 0)
-
-    bounds = property(lambda self: self._bounds)
-    eom_bounds = property(lambda self: self._eom_bounds)
 
     # -- NLP bounds (host-side set-up, opty/direct_collocation.py:370-440) --
     def _generate_constraint_bound_arrays(self):
@@ -1148,8 +1282,22 @@ class Problem(_IpoptBase):
         """(rows, cols), each int64 of shape(nnz,)"""
         return (self.con_jac_rows, self.con_jac_cols)
 
-    def jacobian(self, free):
-        """ndarray, shape(nnz,), aligned with ``jacobianstructure``."""
+    def jacobian(self, free, refetch=False):
+        """ndarray, shape(nnz,), aligned with ``jacobianstructure``.
+
+        Ownership: the array is a view of a pinned host buffer owned by the
+        problem, valid until the next ``jacobian`` / ``constraints`` call --
+        the reference returns a view of its persistent buffer too
+        (opty/direct_collocation.py:2814, 2887) and cyipopt copies it out.
+        Unlike the reference, which rewrites every entry on every call,
+        columns whose value cannot change between calls (literals, and
+        entries that depend on known parameters only when nothing else is
+        free) are copied from the device ONCE.  A consumer that modifies the
+        returned array in place (e.g. scales it) must therefore ask for
+        ``refetch=True`` on the next call, or construct the problem with
+        ``cuda_options={'d2h_skip_constants': False}``."""
+        if refetch:
+            return self.con_jac(free, refetch=True)
         return self.con_jac(free)
 
     def intermediate(self, *args):

@@ -41,7 +41,8 @@ class CollocationProgram(object):
     """
 
     @classmethod
-    def from_matrix(cls, args, expr, const=(), use_sympy_cse=True):
+    def from_matrix(cls, args, expr, const=(), use_sympy_cse=True,
+                    next_args=None):
         """Program that evaluates a matrix of expressions element-wise over
         arrays: the generic operator of ``ufuncify_matrix`` (opty/utils.py:
         639-670).  Non-``const`` args become rows of the trajectory matrix,
@@ -49,10 +50,13 @@ class CollocationProgram(object):
         the place of the Jacobian block and there are no residual outputs.
 
         ``expr`` is a SymPy matrix or the ``(replacements, [matrix])`` pair
-        that ``sm.cse`` returns."""
+        that ``sm.cse`` returns.  ``next_args`` optionally maps an array
+        argument to the symbol that stands for its value at the NEXT point
+        (midpoint-rule integrands read both, :mod:`opty_b200.objective`)."""
         from .lowering import Lowerer
         self = cls.__new__(cls)
         const = tuple(const)
+        next_args = next_args or {}
         T = ir.Tape()
         leaf = {}
         row = 0
@@ -63,6 +67,8 @@ class CollocationProgram(object):
                 uni += 1
             else:
                 leaf[a] = T.vin(2 * row)
+                if a in next_args:
+                    leaf[next_args[a]] = T.vin(2 * row + 1)
                 row += 1
         self.tape = T
         self.R = row

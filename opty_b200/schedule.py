@@ -158,18 +158,36 @@ class BodyDag(object):
         self.children = children
 
         # ---- cost of recomputing a value from the leaves -----------------
-        # (distinct operations + loads in its cone)
-        pos = {v: k for k, v in enumerate(sorted(loads) + nodes)}
+        # (distinct operations + loads in its cone, weighted with the
+        # emitter's issue-slot estimate: a division or a sine is not "one
+        # operation" when it comes to recomputing it)
+        ordered = sorted(loads) + nodes
+        pos = {v: k for k, v in enumerate(ordered)}
+        heavy_mask = 0
+        extra = {}
+        for v in nodes:
+            c = ir.OP_COST.get(op[v], 1)
+            if c > 1:
+                heavy_mask |= 1 << pos[v]
+                extra[pos[v]] = int(c) - 1
         cone = {}
         for v in sorted(loads):
             cone[v] = 1 << pos[v]
+        self.leaf_cost = {}
         for v in nodes:
             m = 1 << pos[v]
             for o in operands(v):
                 if o in cone:
                     m |= cone[o]
             cone[v] = m
-        self.leaf_cost = {v: cone[v].bit_count() for v in cone}
+        for v, m in cone.items():
+            cost = m.bit_count()
+            hv = m & heavy_mask
+            while hv:
+                low = hv & -hv
+                cost += extra[low.bit_length() - 1]
+                hv ^= low
+            self.leaf_cost[v] = cost
         del cone
 
         cheap = set(v for v in values if self.leaf_cost[v] <= inline_cost)

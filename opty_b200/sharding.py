@@ -99,17 +99,35 @@ def gather_vectors(local_con, local_jac, num_collocation_nodes, num_eom,
     """Collective: every rank contributes its shard's residuals and Jacobian
     values (1-D torch tensors on the backend's device: CPU for gloo, CUDA for
     nccl) and receives the full eom-major residual vector and the full
-    node-major Jacobian value vector (EOM parts only)."""
+    node-major Jacobian value vector (EOM parts only).
+
+    With equal shards the node-major Jacobian blocks land directly in the
+    final vector (``all_gather_into_tensor`` into the result, no staging
+    copy) and the eom-major residuals take one gather plus ONE permute
+    ``(G, M, nn) -> (M, G*nn)``; ragged shards (``N - 1`` not divisible by
+    the number of ranks) go through a padded gather."""
     import torch
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     shards = all_shards(num_collocation_nodes, world)
-    K = local_jac.numel() // (shards[dist.get_rank(group)][1] -
-                              shards[dist.get_rank(group)][0])
-    con_blocks = _all_gather_ragged(
-        local_con, [num_eom * (hi - lo) for lo, hi in shards], dist, group)
-    jac_blocks = _all_gather_ragged(
-        local_jac, [K * (hi - lo) for lo, hi in shards], dist, group)
+    sizes = [hi - lo for lo, hi in shards]
+    nn = sizes[rank]
+    K = local_jac.numel() // nn
     total = shards[-1][1]
+    if len(set(sizes)) == 1:
+        jac = torch.empty(total * K, dtype=local_jac.dtype,
+                          device=local_jac.device)
+        dist.all_gather_into_tensor(jac, local_jac.contiguous(), group=group)
+        staged = torch.empty(world * num_eom * nn, dtype=local_con.dtype,
+                             device=local_con.device)
+        dist.all_gather_into_tensor(staged, local_con.contiguous(),
+                                    group=group)
+        con = staged.view(world, num_eom, nn).permute(1, 0, 2).reshape(-1)
+        return con, jac
+    con_blocks = _all_gather_ragged(
+        local_con, [num_eom * n for n in sizes], dist, group)
+    jac_blocks = _all_gather_ragged(
+        local_jac, [K * n for n in sizes], dist, group)
     con = torch.empty((num_eom, total), dtype=local_con.dtype,
                       device=local_con.device)
     for blk, (lo, hi) in zip(con_blocks, shards):

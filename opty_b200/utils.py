@@ -75,3 +75,17 @@ def ufuncify_matrix(args, expr, const=None, tmp_dir=None, parallel=False,
     from .ufuncify import ufuncify_matrix as _impl
     return _impl(args, expr, const=const, tmp_dir=tmp_dir, parallel=parallel,
                  show_compile_output=show_compile_output, **kwargs)
+
+
+def create_objective_function(objective, state_symbols,
+                              unknown_input_trajectories, unknown_parameters,
+                              num_collocation_nodes, node_time_interval,
+                              integration_method='backward euler',
+                              time_symbol=None, **kwargs):
+    """CUDA version of ``opty.utils.create_objective_function``
+    (opty/utils.py:329-470); see :mod:`opty_b200.objective`."""
+    from .objective import create_objective_function as _impl
+    return _impl(objective, state_symbols, unknown_input_trajectories,
+                 unknown_parameters, num_collocation_nodes,
+                 node_time_interval, integration_method=integration_method,
+                 time_symbol=time_symbol, **kwargs)

@@ -259,3 +259,57 @@ def all_cases():
             msd_unknown_trajectory('midpoint'),
             pendulum_instance_constraints(), pendulum_variable_duration(),
             single_eom()]
+
+
+# ---------------------------------------------------------------------------
+# objective functions (opty/utils.py:329-470): the forms of the reference's
+# tests (opty/tests/test_utils.py:67-220) and a tracking objective of the
+# size of BASELINE config 2
+# ---------------------------------------------------------------------------
+def objective_cases():
+    def small(method, which):
+        def make():
+            t = sm.symbols('t')
+            x, v, f1, f2 = [f(t) for f in sm.symbols('x, v, f1, f2',
+                                                      cls=sm.Function)]
+            m, c, k = sm.symbols('m, c, k')
+            exprs = {
+                'single_state': sm.Integral(x ** 2, t),
+                'single_input': sm.Integral(f1 ** 2, t),
+                'single_unknown': m ** 2,
+                'all': (sm.Integral(x ** 2 + m ** 2, t) +
+                        sm.Integral(c ** 2 * f2 ** 2, t) + sm.sin(k) ** 2),
+                'mixed': (3 * sm.Integral(sm.sin(x) * f1 * k +
+                                          sm.exp(v * c), t) -
+                          2 * sm.Integral(f2 * x, t) + m * k),
+            }
+            N = 20
+            free = np.random.default_rng(11).random(4 * N + 3)
+            return dict(objective=exprs[which], states=[x, v],
+                        inputs=[f2, f1], params=[m, c, k], N=N, h=0.3,
+                        method=method, t=t, free=free)
+        return make
+
+    def tracking(method):
+        def make():
+            t = sm.symbols('t')
+            n, N = 22, 10000
+            xs = [sm.Function('x{}'.format(i))(t) for i in range(n)]
+            F = sm.Function('F')(t)
+            w = sm.symbols('w')
+            expr = sm.Integral(F ** 2 + sum((1 + 0.1 * i) * (x - 0.25 * i) ** 2
+                                            for i, x in enumerate(xs[:11])) +
+                               w * sm.cos(xs[11]) ** 2, t) + (w - 2) ** 2
+            free = np.random.default_rng(12).standard_normal((n + 1) * N + 1)
+            return dict(objective=expr, states=xs, inputs=[F], params=[w],
+                        N=N, h=0.001, method=method, t=t, free=free)
+        return make
+
+    out = {}
+    for method in ('backward euler', 'midpoint'):
+        tag = 'be' if method == 'backward euler' else 'mid'
+        for which in ('single_state', 'single_input', 'single_unknown', 'all',
+                      'mixed'):
+            out['{}_{}'.format(which, tag)] = small(method, which)
+        out['tracking22_{}'.format(tag)] = tracking(method)
+    return out

@@ -61,3 +61,16 @@ def assert_values_close(actual, expected, row_len=None, rtol=1e-10,
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+def canonical_triplets(rows, cols, vals, start):
+    """(row, col, value) triplets of the entries from ``start`` on, sorted by
+    (row, col): the instance-constraint part of a Jacobian, whose order inside
+    one constraint follows Python's set iteration in the reference
+    (opty/direct_collocation.py:2244, 2264) and may differ between
+    processes."""
+    r = np.asarray(rows[start:])
+    c = np.asarray(cols[start:])
+    v = np.asarray(vals[start:], dtype=float)
+    order = np.lexsort((c, r))
+    return r[order], c[order], v[order]

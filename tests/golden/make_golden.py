@@ -98,6 +98,14 @@ if __name__ == '__main__':
     if not only or 'cfg2_small_pendulum10_N40' in only:
         save_full('cfg2_small_pendulum10_N40',
               workloads.n_link_pendulum(10, 40, seed=7))
+    if not only or 'cfg4_periodic_pendulum4_N200' in only:
+        # instance constraints with two function atoms: the order of their
+        # Jacobian entries follows Python's set iteration
+        # (opty/direct_collocation.py:2244, 2264), i.e. the hash seed of the
+        # generating process.  Consumers compare the instance part as a set
+        # of (row, col, value) triplets.
+        save_full('cfg4_periodic_pendulum4_N200',
+                  workloads.n_link_pendulum_periodic(4, 200))
     if not only or 'cfg2_pendulum10_N10000' in only:
         save_sampled('cfg2_pendulum10_N10000',
                  workloads.n_link_pendulum(10, 10000))

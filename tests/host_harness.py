@@ -86,3 +86,70 @@ def host_evaluate(collocator, free, known_traj=None):
     lib.host_eval(uni.ctypes.data_as(dp), traj.ctypes.data_as(dp), N, nn,
                   con.ctypes.data_as(dp), jac.ctypes.data_as(dp))
     return con, jac
+
+
+class HostQuadratureHandle(object):
+    """Stand-in for ``runtime.ColloHandle`` of an objective module: runs the
+    emitted integrand code on the CPU (host shim) and applies the quadrature
+    weights of ``opty_colloc_quadrature`` (csrc/runtime.cu) in NumPy."""
+
+    source = None     # set by ``host_objective`` before the handle is built
+
+    def __init__(self, cfg, cubin):
+        self.cfg = cfg
+        self.lib = compile_for_host(HostQuadratureHandle.source)
+
+    def set_known(self, traj, params):
+        pass
+
+    def quadrature(self, free, h, rule):
+        c = self.cfg
+        N, na, r, P = c.N, c.n, c.r, c.P
+        ldt = N + 16
+        traj = np.zeros((max(na, 1), ldt))
+        traj[:na, :N] = free[:na * N].reshape(na, N)
+        uni = np.concatenate((free[na * N:], [0.0]))
+        con = np.zeros(1)
+        jac = np.zeros(N * P)
+        dp = ctypes.POINTER(ctypes.c_double)
+        self.lib.host_eval.argtypes = [dp, dp, ctypes.c_longlong, ctypes.c_int,
+                                       dp, dp]
+        self.lib.host_eval(uni.ctypes.data_as(dp), traj.ctypes.data_as(dp),
+                           ldt, N, con.ctypes.data_as(dp),
+                           jac.ctypes.data_as(dp))
+        vals = jac.reshape(N, P)
+        i = np.arange(N)
+        if rule == 1:
+            ws = (i < N - 1).astype(float)
+            wt = np.where((i == 0) | (i == N - 1), 0.5, 1.0)
+        else:
+            ws = (i > 0).astype(float)
+            wt = ws
+        keep = ws != 0
+        value = h * np.sum(vals[keep, 0])
+        grad = np.zeros(na * N + r)
+        for a in range(na):
+            grad[a * N:(a + 1) * N] = h * wt * vals[:, 1 + a]
+        for s in range(r):
+            grad[na * N + s] = h * np.sum(vals[keep, 1 + na + s])
+        return value, grad
+
+
+def host_objective(*args, **kwargs):
+    """``opty_b200.objective.create_objective_function`` with the device
+    handle replaced by :class:`HostQuadratureHandle` and nvcc skipped."""
+    from opty_b200 import build, objective
+    real_compile, real_handle = build.compile_module, \
+        objective.runtime.ColloHandle
+
+    def capture(src, flags, **k):
+        HostQuadratureHandle.source = src
+        return (b'', '', False)
+    build.compile_module = capture
+    objective.runtime.ColloHandle = HostQuadratureHandle
+    try:
+        kwargs.setdefault('cuda_options', {})['use_index'] = False
+        return objective.create_objective_function(*args, **kwargs)
+    finally:
+        build.compile_module = real_compile
+        objective.runtime.ColloHandle = real_handle

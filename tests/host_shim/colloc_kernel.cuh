@@ -19,8 +19,8 @@
 
 struct OptyTmaps { int unused; };
 struct OptyParams {
-  double* traj; double* con; double* jac;
-  long long ldt; long long ldc; int n_nodes; int n_cols;
+  double* traj; double* tiled; double* con; double* jac;
+  long long ldt; long long ldc; int n_nodes; int n_cols; int n_tiles; int* work;
 };
 struct Dim3 { unsigned x, y, z; };
 static Dim3 blockIdx, threadIdx;
@@ -77,7 +77,7 @@ extern "C" void host_eval(const double* uni, double* traj, long long ldt, int n_
   threadIdx.x = threadIdx.y = 0; blockIdx.x = blockIdx.y = 0;
   opty_colloc_inv(uni, opty_ci);
   OptyTmaps tm; OptyParams p;
-  p.traj = traj; p.con = con; p.jac = jac; p.ldt = ldt; p.ldc = n_nodes; p.n_nodes = n_nodes; p.n_cols = n_nodes + 1;
+  p.traj = traj; p.tiled = nullptr; p.con = con; p.jac = jac; p.ldt = ldt; p.ldc = n_nodes; p.n_nodes = n_nodes; p.n_cols = n_nodes + 1;
   for (int pg = 0; pg < 300; ++pg)
     for (int i = 0; i < n_nodes; ++i) { blockIdx.x = i; blockIdx.y = pg; opty_colloc_pre(p); }
   for (int g = 0; g < OPTY_NGROUPS; ++g)

@@ -78,3 +78,40 @@ def test_two_gpu_node_shards_with_nccl_allgather(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2,
              join=True)
     assert (tmp_path / 'ok0').exists() and (tmp_path / 'ok1').exists()
+
+
+def test_one_process_two_devices_deliver_the_full_vectors():
+    """``devices=[0, 1]``: one process, one handle per GPU, every shard
+    copies into its slice of one pinned host vector; the result is the
+    single-device result bit for bit, instance constraints included."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from conftest import assert_values_close
+    from opty_b200 import ConstraintCollocator
+    from oracle.opty_oracle import OracleCollocator
+    for make in (lambda: workloads.n_link_pendulum_torques(4, 203),
+                 lambda: workloads.n_link_pendulum(10, 40, seed=7)):
+        w = make()
+        one = ConstraintCollocator(*w.collocator_args(),
+                                   **w.collocator_kwargs(), device=0)
+        two = ConstraintCollocator(*w.collocator_args(),
+                                   **w.collocator_kwargs(), devices=[0, 1])
+        free = w.free(one.num_free)
+        con1 = one.generate_constraint_function()(free)
+        jac1 = np.array(one.generate_jacobian_function()(free))
+        con_f = two.generate_constraint_function()
+        jac_f = two.generate_jacobian_function()
+        for point in (free, free * 1.01, free):
+            con2 = con_f(point)
+            jac2 = np.array(jac_f(point))
+        assert np.array_equal(con2, con1)
+        assert np.array_equal(jac2, jac1)
+        r1, c1 = one.jacobian_indices()
+        r2, c2 = two.jacobian_indices()
+        assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
+        orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+        P = orc.P
+        nnz = (orc.N - 1) * orc.M * P
+        assert_values_close(jac2[:nnz], orc.jacobian(free)[:nnz], row_len=P)
+        one.close()
+        two.close()

@@ -15,7 +15,8 @@ import pytest
 import cases
 import gpu_variants
 import workloads
-from conftest import assert_values_close, load_golden
+from conftest import (assert_values_close, canonical_triplets,
+                      load_golden)
 from opty_b200 import ConstraintCollocator, Problem, runtime
 from oracle.opty_oracle import OracleCollocator
 
@@ -457,6 +458,87 @@ def test_callable_known_trajectory_sees_free():
     expected = case.expected_con.copy()
     expected[3:] -= case.free[0]
     np.testing.assert_allclose(con, expected, rtol=1e-12)
+    col.close()
+
+
+def test_two_atom_instance_constraints_against_reference_and_oracle():
+    """Periodicity instance constraints with two function atoms each
+    (examples-gallery/advanced/plot_human_gait.py:163-184), free node time
+    interval, unknown parameters, a known trajectory: against the reference's
+    fixture (instance part as a set of triplets: its order is Python's set
+    iteration order in the generating process, opty/direct_collocation.py:
+    2244, 2264) and, in this process, entry for entry against the oracle."""
+    gold = load_golden('cfg4_periodic_pendulum4_N200')
+    w = workloads.n_link_pendulum_periodic(4, 200)
+    col = _collocator(w)
+    free = w.free(col.num_free)
+    assert np.array_equal(free, gold['free'])
+    con = col.generate_constraint_function()(free)
+    jac = np.array(col.generate_jacobian_function()(free))
+    rows, cols = col.jacobian_indices()
+    nn, M = _eom_sizes(col)
+    P = col._evaluator.program.P
+    nnz = nn * M * P
+    assert len(con) == len(gold['con']) and len(jac) == len(gold['jac'])
+    assert_values_close(con[:M * nn], gold['con'][:M * nn])
+    np.testing.assert_allclose(con[M * nn:], gold['con'][M * nn:],
+                               rtol=1e-13, atol=1e-15)
+    assert_values_close(jac[:nnz], gold['jac'][:nnz], row_len=P)
+    assert np.array_equal(rows[:nnz], gold['rows'][:nnz])
+    assert np.array_equal(cols[:nnz], gold['cols'][:nnz])
+    got = canonical_triplets(rows, cols, jac, nnz)
+    want = canonical_triplets(gold['rows'], gold['cols'], gold['jac'], nnz)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    np.testing.assert_allclose(got[2], want[2], rtol=1e-13, atol=1e-15)
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    orows, ocols = orc.jacobian_indices()
+    assert np.array_equal(rows, orows) and np.array_equal(cols, ocols)
+    np.testing.assert_allclose(jac[nnz:], orc.jacobian(free)[nnz:],
+                               rtol=1e-13, atol=1e-15)
+    col.close()
+
+
+def test_known_parameter_map_is_read_on_every_call():
+    """The reference merges ``known_parameter_map`` / ``known_trajectory_map``
+    into the arguments on every call (opty/direct_collocation.py:2973-2980):
+    changing a value between two evaluations must change the results, for the
+    collocation part and for the host-side instance constraints alike."""
+    w = workloads.n_link_pendulum_torques(4, 200)
+    col = _collocator(w)
+    free = w.free(col.num_free)
+    con_f = col.generate_constraint_function()
+    jac_f = col.generate_jacobian_function()
+    con0 = con_f(free)
+    jac0 = np.array(jac_f(free))
+    key = [p for p in w.known_parameter_map if p.name == 'l1'][0]
+    w.known_parameter_map[key] *= 1.5
+    traj_key = list(w.known_trajectory_map)[0]
+    w.known_trajectory_map[traj_key] = w.known_trajectory_map[traj_key] + 0.5
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    con1 = con_f(free)
+    jac1 = np.array(jac_f(free))
+    assert not np.array_equal(con0, con1)
+    assert not np.array_equal(jac0, jac1)
+    nn, M = _eom_sizes(col)
+    P = col._evaluator.program.P
+    assert_values_close(con1[:M * nn], orc.constraints(free)[:M * nn])
+    assert_values_close(jac1[:nn * M * P], orc.jacobian(free)[:nn * M * P],
+                        row_len=P)
+    col.close()
+
+
+def test_jacobian_refetch_restores_columns_a_consumer_overwrote():
+    w = workloads.n_link_pendulum(10, 40, seed=7)
+    col = _collocator(w)
+    free = w.free(col.num_free)
+    jac_f = col.generate_jacobian_function()
+    ref = np.array(jac_f(free))
+    view = jac_f(free * 1.01)
+    view *= 2.0                       # a consumer scales the buffer in place
+    view = jac_f(free * 1.01)
+    view[:] = 7.0
+    again = np.array(jac_f(free, refetch=True))
+    assert np.array_equal(again, ref)
     col.close()
 
 

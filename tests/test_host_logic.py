@@ -590,3 +590,42 @@ def test_product_package_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert 'oracle' not in text.lower(), fn
                 assert 'host_harness' not in text, fn
+
+
+# ---------------------------------------------------------------------------
+# objective / gradient (opty/utils.py:329-470): symbolic half on the CPU
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('name', [k for k in cases.objective_cases()
+                                  if not k.startswith('tracking')])
+def test_objective_lowering_matches_reference(name):
+    """Integrand, partials, quadrature weights and the parameter-only terms
+    against values produced by the reference's create_objective_function
+    (tests/golden/make_golden_objective.py); the emitted integrand code runs
+    on the CPU through the host shim."""
+    from host_harness import host_objective
+    gold = load_golden('objective_cases')
+    c = cases.objective_cases()[name]()
+    obj, grad = host_objective(
+        c['objective'], c['states'], c['inputs'], c['params'], c['N'],
+        c['h'], integration_method=c['method'], time_symbol=c['t'])
+    np.testing.assert_allclose(obj(c['free']), gold[name + '_value'],
+                               rtol=1e-13)
+    np.testing.assert_allclose(grad(c['free']), gold[name + '_grad'],
+                               rtol=1e-12, atol=1e-15)
+
+
+def test_objective_rejects_what_the_reference_rejects():
+    from opty_b200.utils import create_objective_function
+    t = sm.symbols('t')
+    x = sm.Function('x')(t)
+    with pytest.raises(NotImplementedError):
+        create_objective_function(sm.Integral(x ** 2, t), [x], [], [], 10, 1.0,
+                                  integration_method='not_existing_method',
+                                  time_symbol=t)
+    with pytest.raises(NotImplementedError):
+        create_objective_function(sm.Integral(x ** 2, (t, 0, 1)), [x], [], [],
+                                  10, 1.0, time_symbol=t)
+    with pytest.raises(NotImplementedError):
+        create_objective_function(
+            sm.Integral(sm.Integral(x, t) * x, t), [x], [], [], 10, 1.0,
+            time_symbol=t)

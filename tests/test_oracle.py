@@ -9,7 +9,8 @@ import pytest
 
 import cases
 import workloads
-from conftest import assert_values_close, load_golden
+from conftest import (assert_values_close, canonical_triplets,
+                      load_golden)
 from oracle.opty_oracle import OracleCollocator, forward_jacobian
 
 
@@ -178,3 +179,26 @@ def test_lambdify_oracle_sampled_entries_agree_with_full_evaluation():
     rref = np.array([con[e[1], e[0]] for e in entries])
     assert np.all(np.abs(res - rref) <= 1e-10 * np.abs(rref) +
                   1e-14 * np.abs(con).max())
+
+
+def test_oracle_two_atom_instance_constraints_match_reference():
+    """Periodicity constraints ``x(0) - y(T)`` (examples-gallery/advanced/
+    plot_human_gait.py:163-184): two function atoms per constraint.  EOM part
+    bit for bit in order; the instance part as (row, col, value) triplets."""
+    gold = load_golden('cfg4_periodic_pendulum4_N200')
+    w = workloads.n_link_pendulum_periodic(4, 200)
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    free = w.free(orc.num_free)
+    assert np.array_equal(free, gold['free'])
+    assert np.array_equal(orc.constraints(free), gold['con'])
+    jac = orc.jacobian(free)
+    rows, cols = orc.jacobian_indices()
+    nnz = (orc.N - 1) * orc.M * orc.P
+    assert len(jac) - nnz == 18 and orc.o == 10
+    assert np.array_equal(jac[:nnz], gold['jac'][:nnz])
+    assert np.array_equal(rows[:nnz], gold['rows'][:nnz])
+    assert np.array_equal(cols[:nnz], gold['cols'][:nnz])
+    got = canonical_triplets(rows, cols, jac, nnz)
+    want = canonical_triplets(gold['rows'], gold['cols'], gold['jac'], nnz)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)

@@ -161,3 +161,39 @@ def n_link_pendulum_torques(links=4, num_nodes=2000, method='backward euler',
                     known_parameter_map=par_map,
                     known_trajectory_map=traj_map,
                     instance_constraints=instance, seed=seed, free=draw)
+
+
+def n_link_pendulum_periodic(links=4, num_nodes=200, seed=6):
+    """The config-4 stand-in with the PERIODICITY instance constraints of the
+    human-gait example (examples-gallery/advanced/plot_human_gait.py:163-184):
+    free node time interval, constraints that tie a state at the first node
+    to a (different) state at the last node -- two function atoms each, so
+    their Jacobian entries follow the reference's iteration over
+    ``con.atoms(sm.Function)`` (opty/direct_collocation.py:2244, 2264) -- next
+    to single-atom ones and one with a product."""
+    w = n_link_pendulum_torques(links, num_nodes, seed=seed,
+                                name='pendulum{}_periodic_N{}'.format(
+                                    links, num_nodes))
+    h = w.interval
+    t = me.dynamicsymbols._t
+    duration = (num_nodes - 1) * h
+    half = len(w.states) // 2
+    q, u = w.states[:half], w.states[half:]
+    speed = 1.3
+
+    def at(f, when):
+        return f.subs(t, when)
+    instance = [at(q[0], 0 * h) - 0.0,
+                at(q[1], 0 * h) - 0.0,
+                at(q[1], duration) - speed * at(q[0], duration),
+                at(q[2], 0 * h) - at(q[2], duration)]
+    # left / right swap pattern: q_a(0) = q_b(T), q_b(0) = q_a(T)
+    for a, b in ((3, 4),):
+        instance += [at(q[a], 0 * h) - at(q[b], duration),
+                     at(q[b], 0 * h) - at(q[a], duration)]
+    instance += [at(u[0], 0 * h) - at(u[0], duration),
+                 at(u[1], 0 * h) - at(u[2], duration),
+                 at(u[2], 0 * h) - at(u[1], duration),
+                 at(u[3], 0 * h) * at(u[4], duration) - 0.25]
+    w.instance_constraints = tuple(instance)
+    return w
