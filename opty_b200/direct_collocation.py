@@ -120,9 +120,9 @@ class ConstraintCollocator(object):
     ----------------------------
     backend : 'cuda'
     device : int, CUDA device ordinal (default ``LOCAL_RANK`` or 0)
-    devices : sequence of CUDA device ordinals.  The constraint nodes are
-        split into one contiguous shard per device, all driven by this one
-        process; every shard copies its residuals and Jacobian block straight
+    devices : sequence of CUDA device ordinals (an ordinal may repeat: two
+        shards then share that GPU).  The constraint nodes are split into one
+        contiguous shard per entry, all driven by this one process; every shard copies its residuals and Jacobian block straight
         into its slice of ONE pinned host vector, so that ``constraints`` /
         ``jacobian`` return the whole problem's vectors like a single-device
         collocator does.
@@ -190,9 +190,9 @@ class ConstraintCollocator(object):
         self._devices = None
         if devices is not None:
             devices = [int(d) for d in devices]
-            if not devices or len(set(devices)) != len(devices):
+            if not devices:
                 raise ValueError('devices must be a non-empty sequence of '
-                                 'distinct CUDA device ordinals.')
+                                 'CUDA device ordinals.')
             if device is not None and int(device) != devices[0]:
                 raise ValueError('Give either device or devices.')
             device = devices[0]

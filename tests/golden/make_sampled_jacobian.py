@@ -39,7 +39,9 @@ NODES_PER_PAIR = 2
 
 
 def load_workload(links, N, seed):
-    cache = '/tmp/eomcache/eom_{}.pkl'.format(links)
+    cache = os.path.join(ROOT, 'opty_b200', '_cache', 'eom_{}.pkl'.format(links))
+    if not os.path.exists(cache):
+        cache = '/tmp/eomcache/eom_{}.pkl'.format(links)
     w = None
     if os.path.exists(cache):
         # the constants and the free vector are re-drawn from the seed; only

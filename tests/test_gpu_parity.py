@@ -542,6 +542,44 @@ def test_jacobian_refetch_restores_columns_a_consumer_overwrote():
     col.close()
 
 
+@pytest.mark.parametrize('make', [
+    lambda: workloads.n_link_pendulum_periodic(4, 200),
+    lambda: workloads.n_link_pendulum(10, 40, seed=7),
+    lambda: workloads.vyasarayani2011(101, seed=5),
+], ids=['periodic4', 'pendulum10', 'vyasarayani'])
+def test_sharded_handles_fill_one_host_vector(make):
+    """The ``devices=`` path (one process, one handle per shard, every shard
+    copying straight into its slice of one pinned host vector: contiguous
+    Jacobian blocks, M strided residual segments) -- here with three shards
+    on the one GPU of the test box -- reproduces the unsharded vectors bit
+    for bit, instance-constraint tails included."""
+    w = make()
+    one = _collocator(w)
+    many = ConstraintCollocator(*w.collocator_args(), **w.collocator_kwargs(),
+                                devices=[0, 0, 0])
+    free = w.free(one.num_free)
+    con_f, jac_f = (many.generate_constraint_function(),
+                    many.generate_jacobian_function())
+    con1_f, jac1_f = (one.generate_constraint_function(),
+                      one.generate_jacobian_function())
+    for point in (free, free * 1.01, free * 1.01, free):
+        assert np.array_equal(con_f(point), con1_f(point))
+        assert np.array_equal(np.array(jac_f(point)), np.array(jac1_f(point)))
+    # jacobian before constraints at a new point, and a refetch
+    p2 = free * 0.99
+    assert np.array_equal(np.array(jac_f(p2)), np.array(jac1_f(p2)))
+    assert np.array_equal(con_f(p2), con1_f(p2))
+    view = jac_f(p2)
+    view[:] = -1.0
+    assert np.array_equal(np.array(jac_f(p2, refetch=True)),
+                          np.array(jac1_f(p2)))
+    r1, c1 = one.jacobian_indices()
+    r2, c2 = many.jacobian_indices()
+    assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
+    one.close()
+    many.close()
+
+
 def test_c_abi_rejects_bad_configurations():
     w = workloads.vyasarayani2011(101, seed=5)
     col = _collocator(w)

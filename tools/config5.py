@@ -34,6 +34,24 @@ DUMP = os.path.join(ROOT, 'opty_b200', '_cache',
                     'config5_{}_{}.json'.format(LINKS, TAG))
 
 
+def prepared():
+    """True if the module dump and every cubin it names are in the cache."""
+    if not os.path.exists(DUMP):
+        return False
+    try:
+        with open(DUMP) as f:
+            dump = json.load(f)
+        from opty_b200 import build, codegen
+        if dump['meta'].get('emitter_version') != codegen.EMITTER_VERSION or \
+                dump.get('skeleton_digest') != build._header_digest():
+            return False
+        paths = [dump['cubin']] + [em['cubin_path'] for em in
+                                   dump['meta'].get('extra_modules', ())]
+        return all(os.path.getsize(os.path.join(ROOT, p)) > 0 for p in paths)
+    except (OSError, ValueError, KeyError):
+        return False
+
+
 def prepare():
     """OPTY_VARIANTS='[["tag", {opts}], ...]' prepares several kernel
     variants after deriving the equations of motion once."""
@@ -41,7 +59,7 @@ def prepare():
     import workloads
     global OPTS, TAG, DUMP
     t0 = time.time()
-    cache = '/tmp/eomcache/eom_{}.pkl'.format(LINKS)
+    cache = os.path.join(ROOT, 'opty_b200', '_cache', 'eom_{}.pkl'.format(LINKS))
     if os.path.exists(cache) and LINKS in (20, 50):
         # derived equations of motion kept between runs in the build
         # container (tests/golden/make_sampled_jacobian.py)
@@ -87,6 +105,8 @@ def prepare_one(w, derive_s):
     pm.meta.pop('entry_kind', None)
     dump = {
         'meta': pm.meta, 'opts': opts, 'num_nodes_full': N_FULL,
+        'skeleton_digest': __import__('opty_b200.build', fromlist=['x'])
+        ._header_digest(),
         'cubin': os.path.relpath(pm.cubin_path, ROOT),
         'n': col.num_states, 'q': col.num_unknown_input_trajectories,
         'k': col.num_known_input_trajectories,
