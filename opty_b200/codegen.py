@@ -293,13 +293,13 @@ class _GroupLayout(object):
                         if pairable:
                             j1, k1 = divmod(col + 1, P)
                             self.slots.append(('js2', t, ph['buf'], off, w,
-                                               col - s0))
+                                               col - s0, col))
                             self.roots.append((prog.jac[j0][k0],
                                                prog.jac[j1][k1]))
                             col += 2
                         else:
                             self.slots.append(('js1', t, ph['buf'], off, w,
-                                               col - s0))
+                                               col - s0, col))
                             self.roots.append((prog.jac[j0][k0],))
                             col += 1
                         ph['slots'].append(len(self.slots) - 1)
@@ -372,8 +372,11 @@ class _ScheduledWriter(object):
         lines = []
         slots = layout.slots
         phases = layout.phases
-        left = [sum(1 for k in ph['slots'] if slots[k][0] != 'con')
+        deferred = self.sched.deferred
+        left = [sum(1 for k in ph['slots']
+                    if slots[k][0] != 'con' and k not in deferred)
                 for ph in phases]
+        drained = False
         begun = [False] * len(phases)
         num_ops = 0
         since_fence = 0
@@ -419,6 +422,15 @@ class _ScheduledWriter(object):
                 if slot[0] == 'con':
                     lines.append('OPTY_CON({}, {});'.format(slot[2], vals[0]))
                     continue
+                if k in deferred:
+                    # stored straight to global memory, after the tile store
+                    # of the phase that owns the column has completed
+                    if not drained:
+                        lines.append('OPTY_DRAIN_WRITES();')
+                        drained = True
+                    for c, v in enumerate(vals):
+                        lines.append('OPTY_JG({}, {});'.format(slot[6] + c, v))
+                    continue
                 t = slot[1]
                 if not begun[t]:
                     begun[t] = True
@@ -462,7 +474,9 @@ def _emit_group(g):
         sched = schedule.schedule_body(
             prog.tape, layout.roots, stop, phases=phase_lists,
             reassociate=opts['reassociate'], inline_cost=opts['inline_cost'],
-            remat_cost=opts['remat_cost'], live_budget=opts['live_budget'])
+            remat_cost=opts['remat_cost'], live_budget=opts['live_budget'],
+            deferrable=[k for k, sl in enumerate(layout.slots)
+                        if sl[0] != 'con'])
     else:
         # plain order: slots in layout order (phases are contiguous there)
         sched = schedule.plain_order(prog.tape, layout.roots, stop)
@@ -471,7 +485,7 @@ def _emit_group(g):
     meta = {'rows': [gc0 // prog.P, gc1 // prog.P], 'cols': [gc0, gc1],
             'col0': gc0, 'ncols': layout.stored, 'ops': sched.num_ops,
             'statements': num_ops, 'peak_live': sched.peak_live,
-            'phases': len(layout.phases)}
+            'phases': len(layout.phases), 'deferred': len(sched.deferred)}
     return lines, meta
 
 

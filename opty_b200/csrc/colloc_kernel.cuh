@@ -188,6 +188,14 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
   *reinterpret_cast<double2*>(OPTY_TROW(buf, off, w) + (c)) = make_double2((v0), (v1))
 #define OPTY_JS1(buf, off, w, c, v0) OPTY_TROW(buf, off, w)[(c)] = (v0)
 
+// an entry stored straight to global memory (outputs the scheduler moved to the
+// end of the body, schedule.py `deferrable`); OPTY_DRAIN_WRITES comes first:
+// the tile store of the phase that owns the column has then completed
+#define OPTY_JG(col, val)                                                              \
+  do {                                                                                 \
+    if (ctx.active) ctx.jac[(long long)(ctx.node + ctx.lane) * OPTY_K + (col)] = (val); \
+  } while (0)
+
 // first statement of phase `t` (static index inside the body): its staging
 // buffer is free again once at most OPTY_NBUF-1 younger store groups may still
 // be reading theirs
@@ -214,6 +222,11 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
     if (ctx.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); \
     __syncwarp();                                                                     \
   } while (0)
+#define OPTY_DRAIN_WRITES()                                                      \
+  do {                                                                           \
+    if (ctx.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); \
+    __syncwarp();                                                                \
+  } while (0)
 #else
 // shapes TMA cannot describe (odd M*P): the warp copies a sub-tile out itself,
 // one node row per iteration, coalesced
@@ -232,6 +245,7 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
 #define OPTY_DRAIN() \
   do {               \
   } while (0)
+#define OPTY_DRAIN_WRITES() __syncwarp()
 #endif
 
 // dynamic shared memory: [WARPS][NBUF][OPTY_TILE_DOUBLES] staging buffers |
@@ -319,10 +333,12 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
 //
 // The generated kernel body sits between OPTY_KERNEL_BEGIN and OPTY_KERNEL_END
 // and dispatches on `opty_g`.
+#define OPTY_BLOCK_TO_WORK()                         \
+  const int opty_g = opty_group_order[blockIdx.y];   \
+  const int tile_node0 = blockIdx.x * OPTY_THREADS;
 #define OPTY_KERNEL_BEGIN()                          \
   OPTY_SMEM_SETUP()                                  \
-  const int opty_g = opty_group_order[blockIdx.y];   \
-  const int tile_node0 = blockIdx.x * OPTY_THREADS;  \
+  OPTY_BLOCK_TO_WORK()                               \
   OPTY_STAGE_INIT()                                  \
   OPTY_STAGE_INPUT()                                 \
   OPTY_CTX_SETUP()                                   \

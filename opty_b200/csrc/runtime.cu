@@ -408,6 +408,7 @@ int load_module(opty_colloc* h, const void* cubin, bool primary) {
   }
   m.num_groups = info[INFO_GROUPS];
   m.nmaps = info[INFO_NMAPS];
+
   if (m.num_groups < 1 || m.num_groups > OPTY_MAX_GROUPS || m.nmaps < 1 || m.nmaps > kMaxMaps)
     return bail(fail(OPTY_ERR_ARG, "invalid group / tensor-map count in the module info table"));
   for (int i = 0; i < m.nmaps; ++i) {

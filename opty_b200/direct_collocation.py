@@ -51,7 +51,9 @@ DEFAULT_CUDA_OPTIONS = {
     'groups': 'auto',           # number of output groups (grid.y) or 'auto'
     'tile_cols': 'auto',        # columns of one staging buffer: a whole
                                 # equation row up to 64 columns, else 52
-    'tile_bufs': 2,             # staging buffers per warp (1 or 2)
+    'tile_bufs': 1,             # staging buffers per warp (1 or 2; at config 2
+                                # a second buffer costs a resident block per
+                                # SM and 5 us, profiles/r02a_*)
     'warps_per_block': 'auto',  # 2, or 8 when there are enough node tiles x
                                 # groups for >= 6 waves of 8-warp blocks (the
                                 # warps of a block share every instruction

@@ -502,11 +502,12 @@ class Schedule(object):
     :class:`BodyDag` they refer to (which values are registers, which are
     inlined where), the model's peak live count and the operation count."""
 
-    def __init__(self, dag, events, peak):
+    def __init__(self, dag, events, peak, deferred=()):
         self.dag = dag
         self.events = events
         self.peak_live = peak
         self.num_ops = dag.emitted_ops()
+        self.deferred = frozenset(deferred)   # outputs moved to the last phase
 
 
 def _live_profile(dag, events):
@@ -551,7 +552,8 @@ def _live_profile(dag, events):
 
 def schedule_body(tape, outputs, stop=frozenset(), phases=None,
                   reassociate=True, inline_cost=2, remat_cost=24,
-                  live_budget=40, max_gap=4096, min_gap=24, max_passes=40):
+                  live_budget=40, max_gap=4096, min_gap=24, max_passes=40,
+                  deferrable=(), defer_fraction=0.2):
     """Orders the evaluation of ``outputs`` (tape ids, or tuples of tape ids
     for slots that hold several values).
 
@@ -567,8 +569,42 @@ def schedule_body(tape, outputs, stop=frozenset(), phases=None,
     use recomputes the value inline; ``gap`` starts at ``max_gap`` and
     shrinks by 30 % whenever no such interval is left, down to ``min_gap``.
     A body that fits the budget is not touched, so small models pay nothing.
+
+    ``deferrable``: output indices that may be moved to the LAST phase
+    (the emitter then stores them straight to global memory instead of
+    through their phase's staging tile).  An output of an early phase whose
+    cone is more than ``defer_fraction`` of the whole body -- the partial of
+    a multibody equation with respect to its own coordinate collects a term
+    from every body of the chain -- would force all of those terms to be
+    computed before the phase can be flushed and again, or kept alive, for
+    the later phases; moved to the end it accumulates while the other
+    partials are produced.  The moved indices are in ``Schedule.deferred``.
     """
     dag = BodyDag(tape, outputs, stop, reassociate, inline_cost)
+    deferred = []
+    if phases is not None and len(phases) > 1 and deferrable:
+        last = set(phases[-1])
+        total = max(1, len(dag.reg))
+        memo = {}
+
+        def cone_size(k):
+            seen = set()
+            stack = list(dag.out_rops[k])
+            while stack:
+                x = stack.pop()
+                if x in seen:
+                    continue
+                seen.add(x)
+                stack.extend(dag.rops.get(x, ()))
+            return len(seen)
+        for k in deferrable:
+            if k not in last and cone_size(k) > defer_fraction * total:
+                deferred.append(k)
+        if deferred:
+            moved = set(deferred)
+            phases = [[k for k in ph if k not in moved] for ph in phases]
+            phases[-1] = phases[-1] + deferred
+        del memo
     events, peak = _schedule_dag(dag, phases)
     edges = set()
     gap = max_gap
@@ -603,7 +639,7 @@ def schedule_body(tape, outputs, stop=frozenset(), phases=None,
         dag = BodyDag(tape, outputs, stop, reassociate, inline_cost,
                       frozenset(edges))
         events, peak = _schedule_dag(dag, phases)
-    return Schedule(dag, events, peak)
+    return Schedule(dag, events, peak, deferred)
 
 
 def plain_order(tape, outputs, stop=frozenset()):

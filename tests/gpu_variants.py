@@ -11,7 +11,7 @@ CONFIG2_VARIANTS = [
      'min_blocks_per_sm': 2, 'live_budget': 24},
     {'tma_store': False, 'tma_load': False, 'groups': 5},
     {'d2h_skip_constants': False, 'groups': 3, 'out_ring': 3,
-     'tile_bufs': 1, 'min_blocks_per_sm': 3, 'live_budget': 100},
+     'tile_bufs': 2, 'min_blocks_per_sm': 3, 'live_budget': 100},
     {'pre_pass': False, 'groups': 8, 'warps_per_block': 1,
      'min_blocks_per_sm': 8},
     # direct input loads, one staging buffer per warp holding two rows
@@ -22,6 +22,11 @@ CONFIG2_VARIANTS = [
     # 8-warp blocks with direct input loads
     {'groups': 8, 'warps_per_block': 8, 'min_blocks_per_sm': 1,
      'tma_load': 'direct', 'compile_shards': 2},
+    # code-stationary persistent kernel (TMA input / direct input, two
+    # modules)
+    {'persistent': True, 'groups': 11},
+    {'persistent': True, 'groups': 6, 'tma_load': 'direct',
+     'compile_shards': 2, 'tile_bufs': 2},
 ]
 BITWISE = {'fmad': False, 'reassociate': False}
 
@@ -29,10 +34,14 @@ BITWISE = {'fmad': False, 'reassociate': False}
 CONFIG4_VARIANTS = [
     {},
     # odd P (27): a staging buffer holds two equation rows; here cut further
-    {'tile_cols': 20, 'groups': 4, 'tile_bufs': 1},
+    {'tile_cols': 20, 'groups': 4, 'tile_bufs': 2},
     {'schedule': False, 'tma_load': 'direct'},
+    # persistent kernel on a backward-Euler problem with a known trajectory,
+    # free parameters and a free time interval (invariants change per call)
+    {'persistent': True, 'groups': 4, 'warps_per_block': 4,
+     'min_blocks_per_sm': 2},
 ]
-CONFIG4_IDS = ['default', 'narrow_tiles', 'unscheduled']
+CONFIG4_IDS = ['default', 'narrow_tiles', 'unscheduled', 'persistent']
 
 # tests/test_gpu_parity.py::test_node_range_shards_reproduce_the_whole
 CONFIG2_SHARD_BOUNDS = [0, 1, 2500, 7001, 9999]

@@ -49,6 +49,8 @@ static inline double opty_sign(double x) { return (double)((x > 0.0) - (x < 0.0)
   memcpy(ctx.jac + (long long)ctx.node * OPTY_K + (col0), ctx.tile[buf] + (off) / 32, (w) * sizeof(double));
 #define OPTY_FLUSH_END()
 #define OPTY_DRAIN() do { } while (0)
+#define OPTY_DRAIN_WRITES() do { } while (0)
+#define OPTY_JG(col, val) ctx.jac[(long long)ctx.node * OPTY_K + (col)] = (val)
 #define OPTY_THREADS 1
 #define OPTY_PRE_THREADS 1
 #define OPTY_KERNEL_BEGIN() \
