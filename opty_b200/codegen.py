@@ -50,12 +50,26 @@ INFO_MAGIC = 0x4f505459   # 'OPTY'
 INFO_WORDS = 32
 MAX_MAPS = 8
 
+PLAIN_LIVE_LIMIT = 120
+
 SCHEDULE_DEFAULTS = {
-    'schedule': True,       # False: plain emission order (output by output)
+    'schedule': 'auto',     # False: plain emission order (output by output);
+                            # 'auto': schedule a group only if its plain
+                            # order keeps more than PLAIN_LIVE_LIMIT values
+                            # alive (it then cannot stay in registers).  At
+                            # the 10-link pendulum the plain order fits 252
+                            # registers and is 2-3 % faster than any
+                            # scheduled variant (profiles/r02j_*); from 20
+                            # links on it spills
     'reassociate': True,    # sums accumulate in arrival order
-    'live_budget': 40,      # float64 values the schedule may keep alive
+    'live_budget': 56,      # float64 values the schedule may keep alive
     'inline_cost': 2,       # values this cheap are never kept in a register
     'remat_cost': 24,       # values this cheap may be recomputed after a gap
+    'volatile_loads': 'auto',  # input loads the compiler may not merge:
+                            # 'auto' = for bodies of more than 3 000
+                            # operations (they cannot afford the registers a
+                            # merged load pins; small bodies gain more from
+                            # the shorter instruction stream)
     'fence_every': 0,       # > 0: a warp-level memory fence after this many
                             # statements.  ptxas hoists global loads far
                             # ahead of their use to overlap their latency;
@@ -470,7 +484,12 @@ def _emit_group(g):
                           _WORK['tma_store'], _WORK['tile_bufs'], map_index)
     stop = _WORK['stop']
     phase_lists = [ph['slots'] for ph in layout.phases]
-    if opts['schedule']:
+    use_scheduler = opts['schedule']
+    plain = None
+    if use_scheduler == 'auto':
+        plain = schedule.plain_order(prog.tape, layout.roots, stop)
+        use_scheduler = plain.peak_live > PLAIN_LIVE_LIMIT
+    if use_scheduler:
         sched = schedule.schedule_body(
             prog.tape, layout.roots, stop, phases=phase_lists,
             reassociate=opts['reassociate'], inline_cost=opts['inline_cost'],
@@ -479,13 +498,14 @@ def _emit_group(g):
                         if sl[0] != 'con'])
     else:
         # plain order: slots in layout order (phases are contiguous there)
-        sched = schedule.plain_order(prog.tape, layout.roots, stop)
+        sched = plain or schedule.plain_order(prog.tape, layout.roots, stop)
     writer = _ScheduledWriter(prog, _WORK['derived_index'], sched)
     lines, num_ops = writer.lines_for(layout, int(opts['fence_every']))
     meta = {'rows': [gc0 // prog.P, gc1 // prog.P], 'cols': [gc0, gc1],
             'col0': gc0, 'ncols': layout.stored, 'ops': sched.num_ops,
             'statements': num_ops, 'peak_live': sched.peak_live,
-            'phases': len(layout.phases), 'deferred': len(sched.deferred)}
+            'phases': len(layout.phases), 'deferred': len(sched.deferred),
+            'scheduled': bool(use_scheduler)}
     return lines, meta
 
 
@@ -573,6 +593,12 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     w('#define OPTY_TMA_LOAD {}'.format(int(tma_load)))
     w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
     w('#define OPTY_NBUF {}'.format(tile_bufs))
+    vol = opts['volatile_loads']
+    if vol == 'auto':
+        stop_set = set(derived) or None
+        vol = max(prog.range_cost(c0, c1, stop_set)
+                  for c0, c1 in groups[g0:g1]) > 3000
+    w('#define OPTY_VOLATILE_LOADS {}'.format(1 if vol else 0))
     if persistent:
         w('#define OPTY_PERSISTENT 1')
         w('#define OPTY_SM_TABLE {}'.format(num_sms))

@@ -77,9 +77,10 @@ __constant__ double opty_ci[OPTY_NINV];
 
 struct OptyCtx {
 #if OPTY_TMA_LOAD == 2
-  const double* xg;  // this lane's column of the trajectory matrix (row pitch ldt)
+  const double* xg;  // this lane's column of its tile in the tiled trajectory layout (row pitch OPTY_TW)
 #else
   uint32_t xs;       // shared-memory address of this lane's column in its staged segment (row pitch OPTY_XBOX)
+  const double* xp;  // the same as a pointer (plain loads)
 #endif
   long long ldt;
   double* con;       // &con[node of this lane]
@@ -142,10 +143,15 @@ static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map,
 // ---------------------------------------------------------------------------
 // main kernel: operand and output macros used by the generated group bodies
 // ---------------------------------------------------------------------------
-// Input loads are `asm volatile`: every textual load is one load instruction.
-// The scheduler decides where an input is held in a register and where it is
-// read again (schedule.py); a compiler that merged the loads would pin the
-// register for the whole distance between them.
+// Input loads.  With OPTY_VOLATILE_LOADS they are `asm volatile`: every textual
+// load is one load instruction.  The scheduler decides where an input is held
+// in a register and where it is read again (schedule.py); a compiler that
+// merged the loads would pin the register for the whole distance between
+// them -- what large bodies cannot afford.  Small bodies are better off with
+// plain loads that nvcc may merge (fewer instructions to fetch).
+#ifndef OPTY_VOLATILE_LOADS
+#define OPTY_VOLATILE_LOADS 1
+#endif
 #if OPTY_TMA_LOAD == 2
 // direct mode: no shared-memory staging; the pre-pass kernel lays the
 // trajectory matrix and the derived rows out tile by tile
@@ -156,14 +162,18 @@ static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map,
 // run-time row pitch every row needs its own 64-bit address register; ptxas
 // keeps hundreds of them alive in large bodies and spills.)
 static __device__ __forceinline__ double opty_ldin(const double* p) {
+#if OPTY_VOLATILE_LOADS
   double v;
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
+#else
+  return __ldg(p);
+#endif
 }
 #define XA(r) opty_ldin(ctx.xg + (r) * OPTY_TW)
 #define XB(r) opty_ldin(ctx.xg + (r) * OPTY_TW + 1)
 #define XD(d) opty_ldin(ctx.xg + (OPTY_R + (d)) * OPTY_TW)
-#else
+#elif OPTY_VOLATILE_LOADS
 static __device__ __forceinline__ double opty_ldin(uint32_t a) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
@@ -172,6 +182,10 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
 #define XA(r) opty_ldin(ctx.xs + (r) * (OPTY_XBOX * 8))
 #define XB(r) opty_ldin(ctx.xs + (r) * (OPTY_XBOX * 8) + 8)
 #define XD(d) opty_ldin(ctx.xs + (OPTY_R + (d)) * (OPTY_XBOX * 8))
+#else
+#define XA(r) ctx.xp[(r) * OPTY_XBOX]
+#define XB(r) ctx.xp[(r) * OPTY_XBOX + 1]
+#define XD(d) ctx.xp[(OPTY_R + (d)) * OPTY_XBOX]
 #endif
 
 // scheduling fence: no memory operation moves across it (see codegen.py, `fence_every`)
@@ -292,9 +306,10 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
 #define OPTY_CTX_INPUT() \
   ctx.xg = p.tiled + (long long)(tile_node0 / OPTY_THREADS) * (OPTY_RD * OPTY_TW) + threadIdx.x;
 #else
-#define OPTY_CTX_INPUT()                                                                \
-  ctx.xs = opty_smem_u32(xin_bytes + (threadIdx.x / OPTY_XSEG) * OPTY_XSEG_BYTES) +    \
-           (threadIdx.x % OPTY_XSEG) * 8;
+#define OPTY_CTX_INPUT()                                                                          \
+  ctx.xp = reinterpret_cast<const double*>(xin_bytes + (threadIdx.x / OPTY_XSEG) * OPTY_XSEG_BYTES) + \
+           (threadIdx.x % OPTY_XSEG);                                                             \
+  ctx.xs = opty_smem_u32(ctx.xp);
 #endif
 
 #define OPTY_SMEM_SETUP()                                                                                \

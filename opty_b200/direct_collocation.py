@@ -58,7 +58,8 @@ DEFAULT_CUDA_OPTIONS = {
                                 # groups for >= 6 waves of 8-warp blocks (the
                                 # warps of a block share every instruction
                                 # fetch: large models are bound by that)
-    'min_blocks_per_sm': 'auto',  # launch bound: 16 warps per SM
+    'min_blocks_per_sm': 'auto',  # launch bound: 16 warps per SM when the
+                                # scheduler is on (128 registers), 8 otherwise
     'fmad': True,               # FMA contraction (False: mul/add stay unfused
                                 # like gcc -O2 on x86-64)
     'maxrregcount': None,
@@ -72,17 +73,20 @@ DEFAULT_CUDA_OPTIONS = {
                                 # stays in the instruction cache) and pull
                                 # tiles from per-group atomic counters
     'pre_pass': True,           # shared expensive sub-expressions once per node
-    'schedule': True,           # register-pressure scheduler (schedule.py);
-                                # False: outputs in column order, temporaries
-                                # depth-first before their first use
+    'schedule': 'auto',         # register-pressure scheduler (schedule.py):
+                                # 'auto' = for groups whose plain order keeps
+                                # more than 120 values alive; False: outputs
+                                # in column order, temporaries depth-first
+                                # before their first use
     'reassociate': True,        # sums accumulate their terms in arrival order
                                 # (False: the association order of the
                                 # reference's C printer is kept, results are
                                 # then independent of grouping and tiling)
-    'live_budget': 40,          # float64 values a body may keep alive before
+    'live_budget': 56,          # float64 values a body may keep alive before
                                 # the scheduler starts recomputing cheap ones
     'inline_cost': 2,
     'remat_cost': 24,
+    'volatile_loads': 'auto',   # input loads nvcc may not merge (large bodies)
     'fence_every': 0,           # warp-level memory fence every so many
                                 # statements (bounds ptxas' load hoisting)
     'debug_nostore': False,     # measurement aid: skip Jacobian tile stores
@@ -668,7 +672,11 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     wpb = int(wpb)
     mbs = opts['min_blocks_per_sm']
     if mbs == 'auto':
-        mbs = max(1, 16 // wpb)
+        # plain-order bodies need the whole register file of 8 warps
+        light = opts['schedule'] is False or (
+            opts['schedule'] == 'auto' and
+            prog.stats()['varying_cost'] / max(len(parts), 1) < 1500)
+        mbs = max(1, (8 if light else 16) // wpb)
     mbs = int(mbs)
     tile_cols = codegen.choose_tile_cols(opts['tile_cols'], prog.P,
                                          even=tma_store)
@@ -1063,6 +1071,15 @@ class _MultiDeviceEvaluator(object):
         first = None
         self.evaluators = []
         for part in self.children:
+            if first is not None:
+                # every shard runs the same generated code as the first one
+                # (the automatic geometry depends on the shard size; sums
+                # accumulated in a different order would differ in the last
+                # bit between neighbouring shards)
+                part._cuda_options = dict(
+                    part._cuda_options, groups=len(first.parts),
+                    warps_per_block=first.meta['warps_per_block'],
+                    min_blocks_per_sm=first.meta['min_blocks_per_sm'])
             ev = _CudaEvaluator(part)
             self.evaluators.append(ev)
             first = first or ev
