@@ -275,6 +275,77 @@ def _cpu_baseline_child(budget_s):
             'detail': out}
 
 
+def config5_strong_scaling(rank, world, local_rank, dist, torch):
+    """BASELINE configs[4]: the 50-link chain at 50 000 midpoint nodes (8.49 GB
+    of residuals + Jacobian per evaluation), its nodes sharded over the GPUs
+    of the run (STRONG scaling: the problem does not grow), device resident,
+    plus -- for N > 1 -- the NCCL all-gather of the shards' blocks into the
+    full vectors on every GPU.  Reported as an extra key next to the headline;
+    needs the module prepared by ``__graft_entry__.build()``."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import config5
+    from opty_b200.sharding import _CudaArray, gather_vectors, node_shard
+    if not config5.prepared():
+        return {'skipped': 'config 5 module not prepared'}
+    with open(config5.DUMP) as f:
+        dump = json.load(f)
+    n, q, M, P = dump['n'], dump['q'], dump['M'], dump['P']
+    N_full = dump['num_nodes_full']
+    free = config5.full_free_vector(dump)
+    lo, hi = node_shard(N_full, rank, world)
+    h = config5.make_handle(dump, N_full, (lo, hi), local_rank)
+    h.upload_free(free)
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    h.time_device_evals(2)
+    sync()
+    ms = max_over_ranks(min(h.time_device_evals(5) / 5 for _ in range(3)))
+    nnf = N_full - 1
+    K = M * P
+    B = 8 * ((n + q) * N_full + M * nnf + nnf * K)
+    out = {'workload': 'configs[4]: 50-link chain, {} midpoint nodes, node '
+                       'shards over {} GPU(s), strong scaling'.format(
+                           N_full, world),
+           'device_ms_per_eval': ms, 'algorithmic_GB': B / 1e9,
+           'achieved_GBps_aggregate': B / ms / 1e6,
+           'evals_per_s': 1e3 / ms}
+    if dist is not None and nnf % world == 0:
+        h.eval_device(sync=True)
+        bufs = h.device_buffers()
+        dev = torch.device('cuda', local_rank)
+        con = torch.as_tensor(_CudaArray(bufs['con'], h.con_len, h),
+                              device=dev)
+        jac = torch.as_tensor(_CudaArray(bufs['jac'], h.jac_len, h),
+                              device=dev)
+        full_con, full_jac = gather_vectors(con, jac, N_full, M, dist)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            full_con, full_jac = gather_vectors(con, jac, N_full, M, dist)
+        sync()
+        gather_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / 3)
+        ok = bool(torch.equal(full_jac[lo * K:hi * K], jac))
+        out.update({
+            'nccl_allgather_ms': gather_ms,
+            'allgather_busbw_GBps': (full_jac.numel() * 8 / 1e9) *
+            (world - 1) / world / (gather_ms * 1e-3),
+            'own_block_intact_after_gather': ok})
+        del full_con, full_jac
+    h.close()
+    return out
+
+
 def run_own_arm(args, rank, world, local_rank):
     import torch
     from opty_b200 import ConstraintCollocator
@@ -387,6 +458,14 @@ def run_own_arm(args, rank, world, local_rank):
 
     clocks = sampler.stop() if sampler is not None else None
 
+    extra5 = None
+    if not args.no_config5:
+        try:
+            extra5 = config5_strong_scaling(rank, world, local_rank, dist,
+                                            torch)
+        except Exception as err:  # the headline must not depend on it
+            extra5 = {'failed': '{}: {}'.format(type(err).__name__, err)}
+
     if rank == 0:
         peak, peak_kind = _peaks()
         bytes_launch = algorithmic_bytes(
@@ -455,6 +534,7 @@ def run_own_arm(args, rank, world, local_rank):
                     'how': e2e_how},
             'gpu_launches': int(launches),
             'clocks': clocks,
+            'config5_strong_scaling': extra5,
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
@@ -472,6 +552,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-config5', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

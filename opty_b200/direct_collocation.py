@@ -47,6 +47,9 @@ logger = logging.getLogger(__name__)
 
 _METHODS = ('backward euler', 'midpoint')
 
+# longest chain of store phases one output group may hold (prepare_program_module)
+MAX_PHASES_PER_GROUP = 48
+
 DEFAULT_CUDA_OPTIONS = {
     'groups': 'auto',           # number of output groups (grid.y) or 'auto'
     'tile_cols': 'auto',        # columns of one staging buffer: a whole
@@ -652,8 +655,34 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     # with TMA stores a group starts at an even column (odd P: even row)
     align = 2 if tma_store else 1
 
+    tile_cols = codegen.choose_tile_cols(opts['tile_cols'], prog.P,
+                                         even=tma_store)
+    unit_rows = 1 if (prog.P % 2 == 0 or not tma_store) else 2
+    phases_per_unit = len(codegen.row_phases(
+        0, unit_rows * prog.P, tile_cols, pair if unit_rows == 1 else None,
+        tma_store))
+
     def column_parts(stop=None):
         rows = prog.partition_rows(groups, col_align=align, stop=stop)
+        if opts['groups'] == 'auto':
+            # A warp has one tile store in flight per staging buffer, so a
+            # group is a serial chain of its phases.  Balanced by operation
+            # count alone, the 48 kinematic equations of the 50-link chain
+            # (480 operations, 192 store-only phases) form ONE group that
+            # takes 2.6x as long as the heaviest dynamic equation
+            # (profiles/r02k_*): long chains are cut.
+            cut = []
+            for r0, r1 in rows:
+                units = -(-(r1 - r0) // unit_rows)
+                pieces = -(-units * phases_per_unit // MAX_PHASES_PER_GROUP)
+                pieces = max(1, min(pieces, units))
+                step = -(-units // pieces) * unit_rows
+                r = r0
+                while r < r1:
+                    cut.append((r, min(r1, r + step)))
+                    r += step
+            if len(cut) <= runtime.OPTY_MAX_GROUPS:
+                rows = cut
         return [(r0 * prog.P, r1 * prog.P) for r0, r1 in rows]
 
     parts = column_parts()
@@ -678,8 +707,6 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
             prog.stats()['varying_cost'] / max(len(parts), 1) < 1500)
         mbs = max(1, (8 if light else 16) // wpb)
     mbs = int(mbs)
-    tile_cols = codegen.choose_tile_cols(opts['tile_cols'], prog.P,
-                                         even=tma_store)
     tile_bufs = int(opts['tile_bufs'])
     if tma_load != 2:
         # staged input must fit beside the staging buffers in 227 KB of

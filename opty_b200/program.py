@@ -21,6 +21,14 @@ import hashlib
 from . import ir
 from .lowering import lower_matrix
 
+# Cost of one stored Jacobian column in units of one float64 operation, for
+# balancing the output groups.  (12 was tried after the 50-link measurements
+# and rejected: at the 10-link pendulum it pairs the dynamic equations and
+# splits the cheap kinematic group, 34-35 us instead of 30.8,
+# profiles/r02l_*.  Long chains of store-only phases are cut by
+# MAX_PHASES_PER_GROUP in direct_collocation.prepare_program_module instead.)
+STORE_COST = 2.0
+
 
 class CollocationProgram(object):
     """
@@ -213,7 +221,8 @@ class CollocationProgram(object):
         carved = getattr(self, 'carved', None)
         stored = (c1 - c0) if not carved else \
             (c1 - c0) - sum(carved[c0:c1])
-        return self.tape.cost(self.range_nodes(c0, c1, stop)) + 2.0 * stored
+        return (self.tape.cost(self.range_nodes(c0, c1, stop)) +
+                STORE_COST * stored)
 
     def split_heavy(self, cparts, max_cost, col_align=2, min_cols=16,
                     stop=None):
@@ -273,7 +282,8 @@ class CollocationProgram(object):
 
     def row_costs(self):
         T = self.tape
-        return [T.cost(self.group_nodes([j])) + 2.0 * self.row_store_cols(j)
+        return [T.cost(self.group_nodes([j])) +
+                STORE_COST * self.row_store_cols(j)
                 for j in range(self.M)]
 
     def row_store_cols(self, j):
@@ -347,7 +357,7 @@ class CollocationProgram(object):
         # costs are dyadic numbers: the sums do not depend on the order.
         op_cost = [ir.OP_COST[o] for o in self.tape.op]
         row_sets = [frozenset(self.group_nodes([j], stop)) for j in range(M)]
-        row_store = [2.0 * self.row_store_cols(j) for j in range(M)]
+        row_store = [STORE_COST * self.row_store_cols(j) for j in range(M)]
         cost_cache = {}
         chain = {}      # first row -> (end row, node set, node cost, stores)
 

@@ -464,7 +464,8 @@ def test_sharded_modules_compile_for_sm100a_and_carry_their_geometry():
     with tempfile.TemporaryDirectory() as tmp:
         col = ConstraintCollocator(
             *w.collocator_args(), **w.collocator_kwargs(), tmp_dir=tmp,
-            cuda_options={'groups': 6, 'compile_shards': 3})
+            cuda_options={'groups': 6, 'compile_shards': 3,
+                          'schedule': True, 'min_blocks_per_sm': 8})
         pm = col.prepare_module()
         extra = pm.meta['extra_modules']
         assert len(extra) == 2
