@@ -40,7 +40,7 @@ import os
 
 from . import ir, schedule
 
-EMITTER_VERSION = 6
+EMITTER_VERSION = 7
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 KERNEL_HEADER = os.path.join(_HERE, 'csrc', 'colloc_kernel.cuh')
@@ -467,6 +467,74 @@ class _ScheduledWriter(object):
         return lines, num_ops
 
 
+_INPUT_REF = __import__('re').compile(r'\bX([ABD])\((\d+)\)')
+
+
+def stationary_schedule(costs, n_tiles, n_slots):
+    """Static work assignment of the row-stationary kernel.  ``costs[g]`` is
+    the estimated time of one item (one node tile of a block x group ``g``);
+    every group has ``n_tiles`` items.  Returns one list of segments
+    ``(group, first tile, tiles)`` per slot (= resident block).
+
+    Heavy groups (at least a quarter of the most expensive one) are laid out
+    group by group, tile by tile along the slots in proportion to their cost,
+    so that a block keeps one body -- its instructions stay in the SM's
+    instruction cache from one item, and one launch, to the next.  The light
+    groups (store-only rows such as ``x' = v``) are then dealt out item by
+    item to the least loaded slots and interleaved with the heavy items, which
+    spreads their output over all SMs and over the whole launch."""
+    import heapq
+    G = len(costs)
+    cmax = max(costs) if costs else 1.0
+    heavy = [g for g in range(G) if costs[g] >= 0.25 * cmax]
+    light = [g for g in range(G) if costs[g] < 0.25 * cmax]
+    heavy.sort(key=lambda g: -costs[g])
+    total_heavy = float(sum(costs[g] for g in heavy) * n_tiles) or 1.0
+    per_slot = total_heavy / n_slots
+    load = [0.0] * n_slots
+    hv = [[] for _ in range(n_slots)]
+    cum = 0.0
+    for g in heavy:
+        for t in range(n_tiles):
+            s = min(n_slots - 1, int((cum + 0.5 * costs[g]) / per_slot))
+            cum += costs[g]
+            load[s] += costs[g]
+            if hv[s] and hv[s][-1][0] == g and \
+                    hv[s][-1][1] + hv[s][-1][2] == t:
+                hv[s][-1][2] += 1
+            else:
+                hv[s].append([g, t, 1])
+    lt = [[] for _ in range(n_slots)]
+    heap = [(load[s], s) for s in range(n_slots)]
+    heapq.heapify(heap)
+    for g in light:
+        for t in range(n_tiles):
+            ld, s = heapq.heappop(heap)
+            lt[s].append([g, t, 1])
+            heapq.heappush(heap, (ld + costs[g], s))
+    out = []
+    for s in range(n_slots):
+        # heavy items one by one, a light item after each
+        hitems = [(g, t0 + k) for g, t0, n in hv[s] for k in range(n)]
+        litems = [(g, t) for g, t, _ in lt[s]]
+        seq = []
+        per = -(-len(litems) // max(len(hitems), 1))
+        li = 0
+        for it in hitems:
+            seq.append(it)
+            seq.extend(litems[li:li + per])
+            li += per
+        seq.extend(litems[li:])
+        segs = []
+        for g, t in seq:
+            if segs and segs[-1][0] == g and segs[-1][1] + segs[-1][2] == t:
+                segs[-1][2] += 1
+            else:
+                segs.append([g, t, 1])
+        out.append([tuple(x) for x in segs])
+    return out
+
+
 # shared state of the worker processes that emit group bodies in parallel
 # (set before the pool forks; the tape is far too large to pickle per task)
 _WORK = {}
@@ -494,8 +562,8 @@ def _emit_group(g):
             prog.tape, layout.roots, stop, phases=phase_lists,
             reassociate=opts['reassociate'], inline_cost=opts['inline_cost'],
             remat_cost=opts['remat_cost'], live_budget=opts['live_budget'],
-            deferrable=[k for k, sl in enumerate(layout.slots)
-                        if sl[0] != 'con'])
+            deferrable=[] if _WORK.get('no_defer') else
+            [k for k, sl in enumerate(layout.slots) if sl[0] != 'con'])
     else:
         # plain order: slots in layout order (phases are contiguous there)
         sched = plain or schedule.plain_order(prog.tape, layout.roots, stop)
@@ -533,7 +601,9 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
                 derived=(), debug_nostore=False, tile_bufs=2,
                 only_groups=None, with_aux=True, pair=None,
                 schedule_options=None, workers=1, persistent=False,
-                num_sms=148):
+                num_sms=148, num_nodes=None, blocks_per_sm=1, const_rows=(),
+                const_head_pct=(25, 35, 15), store_hint=0, fused_pre=False,
+                item_cost=16000):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block,
     whole equations each; a group also owns the residuals of its rows).
@@ -551,6 +621,14 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     M, P, K, R = prog.M, prog.P, prog.K, prog.R
     tma_store = bool(tma_store) and K % 2 == 0
     C = choose_tile_cols(tile_cols, P, even=tma_store)
+    persistent = int(persistent)
+    stationary = persistent == 2
+    if stationary:
+        if num_nodes is None or not tma_store or int(tma_load) != 1:
+            raise ValueError('the row-stationary kernel needs the node count, '
+                             'TMA stores and staged (row-major) input')
+        if only_groups is not None:
+            raise ValueError('the row-stationary kernel is one module')
     if warps_per_block > 4 and warps_per_block % 4:
         raise ValueError('warps_per_block above 4 must be a multiple of 4')
     tile_bufs = int(tile_bufs)
@@ -559,6 +637,26 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     opts = dict(SCHEDULE_DEFAULTS)
     opts.update(schedule_options or {})
     ninv = len(prog.inv_nodes)
+    # constant rows (row-stationary kernel): equations whose partials are all
+    # literals or node-invariant values (x' = v and the like).  Their part of
+    # every node's Jacobian row is the same run of numbers: the invariants
+    # kernel appends it to its table, the main kernel copies it to every node
+    # with plain 16-byte stores, the pre-pass evaluates their residuals.
+    const_rows = sorted(const_rows)
+    const_runs = []         # (first column, doubles, offset into the values)
+    const_entries = []
+    for j in const_rows:
+        if const_runs and const_runs[-1][0] + const_runs[-1][1] == j * P:
+            const_runs[-1][1] += P
+        else:
+            const_runs.append([j * P, P, len(const_entries)])
+        const_entries.extend(prog.jac[j])
+    if const_rows and not (stationary and P % 2 == 0):
+        raise ValueError('constant rows need the row-stationary kernel and '
+                         'an even number of partials per equation')
+    cval0 = ninv + (ninv & 1)
+    if const_rows:
+        ninv = cval0 + len(const_entries)
     derived = list(derived)
     derived_index = {nid: k for k, nid in enumerate(derived)}
     D = len(derived)
@@ -593,6 +691,7 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     w('#define OPTY_TMA_LOAD {}'.format(int(tma_load)))
     w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
     w('#define OPTY_NBUF {}'.format(tile_bufs))
+    w('#define OPTY_STORE_HINT {}'.format(int(store_hint)))
     vol = opts['volatile_loads']
     if vol == 'auto':
         stop_set = set(derived) or None
@@ -600,9 +699,22 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
                   for c0, c1 in groups[g0:g1]) > 3000
     w('#define OPTY_VOLATILE_LOADS {}'.format(1 if vol else 0))
     if persistent:
-        w('#define OPTY_PERSISTENT 1')
+        w('#define OPTY_PERSISTENT {}'.format(persistent))
         w('#define OPTY_SM_TABLE {}'.format(num_sms))
-    w('#define OPTY_PRE_GROUPS {}'.format(len(set(T.a[nid] for nid in derived))))
+    if stationary:
+        w('#define OPTY_NSLOTS {}'.format(num_sms * blocks_per_sm))
+        w('#define OPTY_BPS {}'.format(blocks_per_sm))
+        # placeholder, replaced once the bodies' input windows are known
+        w('@@XROWS_MAX@@')
+    w('#define OPTY_PRE_GROUPS {}'.format(
+        len(set(T.a[nid] for nid in derived)) + (1 if const_rows else 0)))
+    w('#define OPTY_NCRUNS {}'.format(len(const_runs)))
+    w('#define OPTY_NCONST {}'.format(len(const_entries)))
+    chead = list(const_head_pct) if isinstance(
+        const_head_pct, (list, tuple)) else [const_head_pct, 35, 15]
+    w('#define OPTY_CONST_HEAD_PCT {}'.format(int(chead[0])))
+    w('#define OPTY_CONST_FIRST_PCT {}'.format(int(chead[1])))
+    w('#define OPTY_CONST_ITEM_PCT {}'.format(int(chead[2])))
     if debug_nostore:
         w('#define OPTY_DEBUG_NOSTORE {}'.format(int(debug_nostore)))
     w('#include "colloc_kernel.cuh"')
@@ -614,6 +726,8 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         bw = _BodyWriter(prog, 'inv')
         for nid in prog.inv_nodes:
             bw.need(nid)
+        for nid in const_entries:
+            bw.need(nid)
         w('extern "C" __global__ void opty_colloc_inv('
           'const double* __restrict__ uni, double* __restrict__ inv)')
         w('{')
@@ -622,6 +736,8 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
             w('  ' + line)
         for k, nid in enumerate(prog.inv_nodes):
             w('  inv[{}] = {};'.format(k, bw.ref(nid)))
+        for k, nid in enumerate(const_entries):
+            w('  inv[{}] = {};'.format(cval0 + k, bw.ref(nid)))
         w('}')
         w('')
         inv_ops = bw.num_ops
@@ -635,35 +751,108 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         by_arg.setdefault(T.a[nid], []).append(k)
     for ks in by_arg.values():
         pre_chunks.append(ks)
-    pre_groups = len(pre_chunks)
+    pre_groups = len(pre_chunks) + (1 if const_rows else 0)
     pre_ops = 0
+    fused_pre = bool(fused_pre) and stationary and with_aux and \
+        0 < pre_groups <= num_sms * blocks_per_sm
+    if fused_pre:
+        out.insert(out.index('#include "colloc_kernel.cuh"'),
+                   '#define OPTY_FUSED_PRE 1')
     if with_aux:
-        w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
-        w('opty_colloc_pre(const OptyParams p)')
-        w('{')
-        w('  OPTY_PRE_BEGIN();')
-        w('  switch (opty_pg) {')
+        case_lines = []
         for pg, ks in enumerate(pre_chunks):
             bw = _BodyWriter(prog, 'pre')
             for k in ks:
                 bw.need(derived[k])
                 bw.lines.append('OPTY_DRV({}, {});'.format(
                     k, bw.ref(derived[k])))
-            w('    case {}: {{'.format(pg))
-            for line in bw.lines:
-                w('      ' + line)
-            w('    } break;')
+            case_lines.append('    case {}: {{'.format(pg))
+            case_lines.extend('      ' + line for line in bw.lines)
+            case_lines.append('    } break;')
             pre_ops += bw.num_ops
+        if const_rows:
+            bw = _BodyWriter(prog, 'pre')
+            # all loads before the first store: the compiler cannot tell that
+            # the residual rows do not alias the trajectory matrix
+            for j in const_rows:
+                bw.need(prog.con[j])
+            for j in const_rows:
+                bw.lines.append('OPTY_PCON({}, {});'.format(
+                    j, bw.ref(prog.con[j])))
+            case_lines.append('    case {}: {{'.format(len(pre_chunks)))
+            case_lines.extend('      ' + line for line in bw.lines)
+            case_lines.append('    } break;')
+            pre_ops += bw.num_ops
+        w('extern "C" __global__ void __launch_bounds__(OPTY_PRE_THREADS)')
+        w('opty_colloc_pre(const OptyParams p)')
+        w('{')
+        w('  OPTY_PRE_BEGIN();')
+        w('  switch (opty_pg) {')
+        for line in case_lines:
+            w(line)
         w('    default: break;')
         w('  }')
         w('}')
         w('')
+        if fused_pre:
+            # the same cases as a device function: phase 0 of the
+            # row-stationary kernel (one case per block)
+            w('static __device__ __forceinline__ void opty_pre_case('
+              'const OptyParams& p, const int* nodes, const int opty_pg)')
+            w('{')
+            w('  switch (opty_pg) {')
+            for line in case_lines:
+                if line.startswith('    case '):
+                    w(line)
+                    w('      _Pragma("unroll") for (int u_ = 0; u_ < '
+                      'OPTY_PRE_ILP; ++u_) {')
+                    w('      const int node = nodes[u_];')
+                    w('      const double* xg = p.traj + node;')
+                    w('      double* drv = p.traj + (long long)OPTY_R * p.ldt '
+                      '+ node;')
+                elif line.startswith('    } break;'):
+                    w('      }')
+                    w(line)
+                else:
+                    w(line)
+            w('    default: break;')
+            w('  }')
+            w('}')
+            w('')
+
+    if stationary:
+        # do the input windows fit?  (before the bodies are scheduled: the
+        # rows a group reads follow from the tape)
+        stop_set = set(derived)
+        rows_max = 1
+        for gc0, gc1 in groups:
+            used = set()
+            for i in prog._reachable_stop(prog.range_roots(gc0, gc1),
+                                          stop_set):
+                if T.op[i] == ir.VIN:
+                    used.add(T.a[i] >> 1)
+                elif i in derived_index:
+                    used.add(R + derived_index[i])
+            if used:
+                rows_max = max(rows_max, max(used) + 1 - min(used))
+        threads = 32 * warps_per_block
+        xseg = min(threads, 128)
+        need = warps_per_block * tile_bufs * 32 * C * 8 + 128 + \
+            2 * (threads // xseg) * (-(-(rows_max * (xseg + 2) * 8) // 128)
+                                     * 128) + \
+            (-(-len(const_entries) * 8 // 128) * 128)
+        if need > 227 * 1024:
+            raise ValueError(
+                'the row-stationary kernel would need {} bytes of shared '
+                'memory per block ({} staging buffers of {} columns for {} '
+                'warps, two input buffers of {} rows)'.format(
+                    need, tile_bufs, C, warps_per_block, rows_max))
 
     # ---- group bodies (scheduled, possibly in parallel) ------------------
     _WORK.update(prog=prog, opts=opts, groups=groups, widths=map_widths,
                  tile_cols=C, pair=pair, tma_store=tma_store,
                  tile_bufs=tile_bufs, stop=frozenset(derived),
-                 derived_index=derived_index)
+                 derived_index=derived_index, no_defer=stationary)
     todo = list(range(g0, g1))
     workers = max(1, min(int(workers), len(todo)))
     if workers > 1:
@@ -675,6 +864,18 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     _WORK.clear()
     group_meta = []
     for g, (lines, gm) in zip(todo, results):
+        if stationary:
+            # input window of the body: the contiguous range of trajectory /
+            # derived rows it reads (staged per item, csrc/colloc_kernel.cuh)
+            used = set()
+            for line in lines:
+                for kind, idx in _INPUT_REF.findall(line):
+                    used.add(int(idx) + (R if kind == 'D' else 0))
+            row0 = min(used) if used else 0
+            gm['xrow0'] = row0
+            gm['xrows'] = (max(used) + 1 - row0) if used else 1
+            w('#undef OPTY_XROW0')
+            w('#define OPTY_XROW0 {}'.format(row0))
         w('static __device__ __forceinline__ void opty_group_{}('
           'const OptyCtx& ctx)'.format(g))
         w('{')
@@ -690,7 +891,7 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
                                    43 * group_meta[g]['ncols']))
     w('__device__ const int opty_group_order[OPTY_NGROUPS] = {{{}}};'.format(
         ', '.join(str(g) for g in order)))
-    if persistent:
+    if persistent == 1:
         # slot = position in opty_group_order.  SMs are dealt out to the
         # slots in proportion to the slots' cost; every block of an SM starts
         # on the SM's slot
@@ -710,6 +911,57 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
             ', '.join(str(v) for v in table)))
         w('__device__ const int opty_slot_cost[OPTY_NGROUPS] = {{{}}};'.format(
             ', '.join(str(max(1, int(c // 100))) for c in costs)))
+    smem_bytes = 0
+    if stationary:
+        threads = 32 * warps_per_block
+        n_tiles = -(-int(num_nodes) // threads)
+        n_slots = num_sms * blocks_per_sm
+        # measured at the 10-link pendulum: an item takes 1.3 us + 1.4 ns per
+        # operation (profiles/r02z_*)
+        costs = [20.0 * gm['ops'] + 43.0 * gm['ncols'] + float(item_cost)
+                 for gm in group_meta]
+        sched = stationary_schedule(costs, n_tiles, n_slots)
+        starts, segs = [0], []
+        for slot in sched:
+            segs.extend(slot)
+            starts.append(len(segs))
+        xrows_max = max(gm['xrows'] for gm in group_meta)
+        out[out.index('@@XROWS_MAX@@')] = \
+            '#define OPTY_XROWS_MAX {}'.format(xrows_max)
+        if const_runs:
+            w('__device__ const int opty_crun[OPTY_NCRUNS][3] = {{{}}};'.format(
+                ', '.join('{{{}, {}, {}}}'.format(c0, n // 2, off)
+                          for c0, n, off in const_runs)))
+        w('__device__ const int opty_group_xrow0[OPTY_NGROUPS] = {{{}}};'.format(
+            ', '.join(str(gm['xrow0']) for gm in group_meta)))
+        w('__device__ const int opty_group_xrows[OPTY_NGROUPS] = {{{}}};'.format(
+            ', '.join(str(gm['xrows']) for gm in group_meta)))
+        w('__device__ const int opty_group_odd[OPTY_NGROUPS] = {{{}}};'.format(
+            ', '.join(str(gm['phases'] & 1) for gm in group_meta)))
+        # (constant memory while the tables are small: the first item of a
+        # block waits for them)
+        space = '__constant__' if len(segs) <= 2048 else '__device__ const'
+        w('{} int opty_sched_slot[OPTY_NSLOTS + 1] = {{{}}};'
+          .format(space, ', '.join(str(v) for v in starts)))
+        w('{} int4 opty_sched_seg[{}] = {{{}}};'.format(space, 
+            max(len(segs), 1),
+            ', '.join('{{{}, {}, {}, {}}}'.format(
+                g, t0, nt, group_meta[g]['xrow0'] |
+                (group_meta[g]['xrows'] << 16)) for g, t0, nt in segs) or
+            '{0, 0, 0, 0}'))
+        xseg = min(threads, 128)
+        xbuf = (threads // xseg) * (
+            -(-(xrows_max * (xseg + 2) * 8) // 128) * 128)
+        smem_bytes = warps_per_block * tile_bufs * 32 * C * 8 + 2 * xbuf + 128
+        if const_runs:
+            smem_bytes += -(-len(const_entries) * 8 // 128) * 128
+        if smem_bytes > 227 * 1024:
+            raise ValueError(
+                'the row-stationary kernel needs {} bytes of shared memory per '
+                'block ({} staging buffers of {} columns for {} warps, two '
+                'input buffers of {} rows); use fewer warps, one staging '
+                'buffer or narrower tiles'.format(
+                    smem_bytes, tile_bufs, C, warps_per_block, xrows_max))
     w('')
     info = [0] * INFO_WORDS
     info[0] = INFO_MAGIC
@@ -730,8 +982,15 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     info[21] = M
     info[22] = P
     info[23] = 1 if with_aux else 0
-    info[24] = 1 if persistent else 0
+    info[24] = persistent
     info[25] = min_blocks_per_sm
+    if stationary:
+        info[26] = smem_bytes
+        info[27] = num_sms * blocks_per_sm
+        info[28] = n_tiles
+        info[29] = cval0 if const_rows else 0
+        info[30] = 1 if fused_pre else 0
+        info[31] = xrows_max
     w('extern "C" __device__ const int opty_module_info[{}] = {{{}}};'.format(
         INFO_WORDS, ', '.join(str(v) for v in info)))
     w('')
@@ -768,7 +1027,10 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         'tma_load': int(tma_load),
         'tma_store': bool(tma_store),
         'tile_bufs': tile_bufs,
-        'persistent': bool(persistent),
+        'persistent': persistent,
+        'smem_bytes': smem_bytes,
+        'const_rows': list(const_rows),
+        'fused_pre': bool(fused_pre),
         'method': method,
         'schedule': opts,
         'entry_kind': prog.entry_kind(),

@@ -40,6 +40,7 @@
 
 #include <cuda.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "colloc_params.h"
 
@@ -59,6 +60,9 @@
 #define OPTY_TW (OPTY_THREADS + 2)  // row pitch of the tiled trajectory layout (direct input loads)
 #define OPTY_NSEG (OPTY_THREADS / OPTY_XSEG)
 #define OPTY_XSEG_BYTES (((OPTY_RD * OPTY_XBOX * 8) + 127) / 128 * 128)
+#ifndef OPTY_PERSISTENT
+#define OPTY_PERSISTENT 0
+#endif
 #ifndef OPTY_NBUF
 #define OPTY_NBUF 2  // staging buffers per warp (phases whose TMA stores may be in flight + 1)
 #endif
@@ -85,6 +89,9 @@ struct OptyCtx {
   long long ldt;
   double* con;       // &con[node of this lane]
   double* tile0;     // the warp's staging buffer 0 (buffer b: + b * OPTY_TILE_DOUBLES)
+#if OPTY_PERSISTENT == 2
+  double* tile1;     // staging buffer 1 (the two swap after an item with an odd number of phases)
+#endif
   double* jac;       // p.jac
   const OptyTmaps* tm;
   long long ldc;
@@ -133,11 +140,32 @@ static __device__ __forceinline__ void opty_tma_load_2d(void* dst, const CUtenso
       : "memory");
 }
 
+// L2 policy of the Jacobian stores.  The output (81 MB per evaluation at BASELINE config 2, 126 MB of L2)
+// is written once and read by nobody on the device; with the default policy every launch pushes the
+// module's code and the trajectory matrix out of L2, and the next launch re-reads both through a cache
+// full of dirty lines.  evict_first makes the freshly written lines the first candidates for replacement.
+#ifndef OPTY_STORE_HINT
+#define OPTY_STORE_HINT 0  // 0 none, 1 evict_first, 2 evict_last (measurement), 3 no_allocate-like evict_unchanged
+#endif
+#if OPTY_STORE_HINT == 1
+#define OPTY_STORE_POLICY 0x12F0000000000000ull
+#elif OPTY_STORE_HINT == 2
+#define OPTY_STORE_POLICY 0x14F0000000000000ull
+#else
+#define OPTY_STORE_POLICY 0x1000000000000000ull
+#endif
 static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+#if OPTY_STORE_HINT
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(opty_smem_u32(src)), "l"(OPTY_STORE_POLICY)
+               : "memory");
+#else
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
                "r"(c0), "r"(c1), "r"(opty_smem_u32(src))
                : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -152,7 +180,26 @@ static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map,
 #ifndef OPTY_VOLATILE_LOADS
 #define OPTY_VOLATILE_LOADS 1
 #endif
-#if OPTY_TMA_LOAD == 2
+#if OPTY_PERSISTENT == 2
+// row-stationary kernel: the block's input buffer holds the rows
+// OPTY_XROW0 .. of the item's group (the emitter defines OPTY_XROW0 in front of
+// every body) in segments of OPTY_XSEG nodes, row pitch OPTY_XBOX doubles
+#define OPTY_PXBOX OPTY_XBOX
+#if OPTY_VOLATILE_LOADS
+static __device__ __forceinline__ double opty_ldin(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+#define XA(r) opty_ldin(ctx.xs + ((r) - OPTY_XROW0) * (OPTY_PXBOX * 8))
+#define XB(r) opty_ldin(ctx.xs + ((r) - OPTY_XROW0) * (OPTY_PXBOX * 8) + 8)
+#define XD(d) opty_ldin(ctx.xs + ((OPTY_R + (d)) - OPTY_XROW0) * (OPTY_PXBOX * 8))
+#else
+#define XA(r) ctx.xp[((r) - OPTY_XROW0) * OPTY_PXBOX]
+#define XB(r) ctx.xp[((r) - OPTY_XROW0) * OPTY_PXBOX + 1]
+#define XD(d) ctx.xp[((OPTY_R + (d)) - OPTY_XROW0) * OPTY_PXBOX]
+#endif
+#elif OPTY_TMA_LOAD == 2
 // direct mode: no shared-memory staging; the pre-pass kernel lays the
 // trajectory matrix and the derived rows out tile by tile
 // ([tiles][R + D][OPTY_TW], OPTY_TW = nodes of a block + 2), so that every row
@@ -197,7 +244,12 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
   } while (0)
 
 // this lane's row of the sub-tile that starts `off` doubles into staging buffer `buf` and is `w` columns wide
-#define OPTY_TROW(buf, off, w) (ctx.tile0 + (buf) * OPTY_TILE_DOUBLES + (off) + ctx.lane * (w))
+#if OPTY_PERSISTENT == 2
+#define OPTY_TBUF(buf) ((buf) ? ctx.tile1 : ctx.tile0)
+#else
+#define OPTY_TBUF(buf) (ctx.tile0 + (buf) * OPTY_TILE_DOUBLES)
+#endif
+#define OPTY_TROW(buf, off, w) (OPTY_TBUF(buf) + (off) + ctx.lane * (w))
 #define OPTY_JS2(buf, off, w, c, v0, v1) \
   *reinterpret_cast<double2*>(OPTY_TROW(buf, off, w) + (c)) = make_double2((v0), (v1))
 #define OPTY_JS1(buf, off, w, c, v0) OPTY_TROW(buf, off, w)[(c)] = (v0)
@@ -214,9 +266,11 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
 // buffer is free again once at most OPTY_NBUF-1 younger store groups may still
 // be reading theirs
 #if OPTY_TMA_STORE
+// (row-stationary kernel: a warp's store groups run on from item to item, so
+// every phase waits)
 #define OPTY_PHASE_BEGIN(t)                                                                                   \
   do {                                                                                                        \
-    if ((t) >= OPTY_NBUF) {                                                                                   \
+    if ((t) >= OPTY_NBUF || OPTY_PERSISTENT == 2) {                                                           \
       if (ctx.lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(OPTY_NBUF - 1) : "memory"); \
       __syncwarp();                                                                                           \
     }                                                                                                         \
@@ -227,15 +281,21 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
   __syncwarp();
 #define OPTY_TSTORE(map, buf, off, w, col0)                                                                   \
-  if (ctx.lane == 0 && OPTY_DEBUG_NOSTORE != 1)                                                               \
-    opty_tma_store_2d(&ctx.tm->out[map], ctx.tile0 + (buf) * OPTY_TILE_DOUBLES + (off), (col0), ctx.node);
+  if (ctx.lane == 0 && (OPTY_DEBUG_NOSTORE & 1) == 0)                                                               \
+    opty_tma_store_2d(&ctx.tm->out[map], OPTY_TBUF(buf) + (off), (col0), ctx.node);
 #define OPTY_FLUSH_END() \
   if (ctx.lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#if OPTY_PERSISTENT == 2
+#define OPTY_DRAIN() \
+  do {               \
+  } while (0)
+#else
 #define OPTY_DRAIN()                                                                  \
   do {                                                                                \
     if (ctx.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); \
     __syncwarp();                                                                     \
   } while (0)
+#endif
 #define OPTY_DRAIN_WRITES()                                                      \
   do {                                                                           \
     if (ctx.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); \
@@ -336,10 +396,6 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
   ctx.active = (tile_node0 + (int)threadIdx.x) < p.n_nodes;               \
   ctx.con = p.con + tile_node0 + threadIdx.x;
 
-#ifndef OPTY_PERSISTENT
-#define OPTY_PERSISTENT 0
-#endif
-
 #if !OPTY_PERSISTENT
 // Grid kernel: one block = one tile of 32*W nodes x one output group; grid =
 // (tiles, groups).  blockIdx.y walks the groups in the order the emitter chose
@@ -360,6 +416,294 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
   if (ctx.node >= p.n_nodes) return;
 
 #define OPTY_KERNEL_END()
+
+#elif OPTY_PERSISTENT == 2
+// Row-stationary persistent kernel: grid = OPTY_NSLOTS resident blocks (one per
+// SM).  The emitter lays the work out statically (codegen.stationary_schedule):
+// a slot is a list of segments (group, first node tile, tiles); heavy groups
+// -- one equation row each -- keep their slots for the whole launch, so an SM
+// executes ONE body, tile after tile and launch after launch, out of its
+// instruction cache (a block takes the slot of its %smid; the grid kernel
+// above streams 25-55 KB of once-used code per block through the GPC-level
+// instruction caches and spends > 60 % of its stall samples waiting for
+// instructions, profiles/).  Everything else a body needs from L2 is taken off
+// its critical path as well:
+//   * the input rows of the NEXT item (the contiguous row window the body reads,
+//     opty_group_xrow0/xrows) are fetched by bulk copies
+//     (cp.async.bulk.shared.global, one row of OPTY_THREADS + 2 columns per
+//     lane of warp 0, mbarrier completion) into the second input buffer while
+//     the block works on the current item;
+//   * a warp's Jacobian tile stores run on across items: staging buffers
+//     alternate (an item with an odd number of phases swaps them), a phase only
+//     waits until the store before the previous one has read its buffer.
+// All warps of a block run the same body on adjacent node tiles; one
+// __syncthreads per item hands the consumed input buffer back to the prefetch.
+#define OPTY_PXSEG_BYTES (((OPTY_XROWS_MAX * OPTY_XBOX * 8) + 127) / 128 * 128)
+#define OPTY_XBUF_BYTES (OPTY_NSEG * OPTY_PXSEG_BYTES)
+#undef OPTY_SMEM_XIN_BYTES
+#define OPTY_SMEM_XIN_BYTES (2 * OPTY_XBUF_BYTES)
+
+// one lane: fetch the input window (OPTY_XROWS_MAX rows from row0) of node tile t into `dst` -- one 2-D TMA
+// tile load per segment of OPTY_XSEG nodes (tm.in: box {OPTY_XBOX, OPTY_XROWS_MAX}; rows and columns beyond
+// the matrix arrive as zeros).  (One bulk copy per row and lane was tried first: the 32 copies of a warp
+// are issued one after the other and kept warp 0 a microsecond behind the others in every item.)
+static __device__ __forceinline__ void opty_issue_input_rows(const CUtensorMap* map, int row0, int t,
+                                                             unsigned char* dst, uint64_t* bar) {
+  opty_mbar_expect_tx(bar, OPTY_NSEG * OPTY_XROWS_MAX * OPTY_XBOX * 8);
+  for (int sgm = 0; sgm < OPTY_NSEG; ++sgm)
+    opty_tma_load_2d(dst + sgm * OPTY_PXSEG_BYTES, map, t * OPTY_THREADS + sgm * OPTY_XSEG, row0, bar);
+}
+// (the window of a segment's group is packed into the segment entry: .w = first row | rows << 16)
+#define opty_issue_input(p, sg, t, dst, bar) \
+  if ((threadIdx.x & 31) == 0) opty_issue_input_rows(&tm.in, (sg).w & 0xffff, t, dst, bar)
+
+// Phase 0 (OPTY_FUSED_PRE): the derived rows and the residuals of the constant rows -- the work of the
+// pre-pass kernel -- are computed by the blocks of this launch: block = one case of the pre-pass (its code
+// stays small) x one chunk of the nodes.  `p.ready[0]` counts the (node, case) pairs done over all launches
+// of the handle (64-bit, never reset); a block fetches its first input window once the count has reached
+// this launch's target.  All blocks are resident (one per SM) and produce before they consume.
+#ifndef OPTY_FUSED_PRE
+#define OPTY_FUSED_PRE 0
+#endif
+#if OPTY_FUSED_PRE
+static __device__ __forceinline__ unsigned long long opty_ld_acquire(const unsigned long long* a) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+  return v;
+}
+// warp 0, before it fetches its first input window: every (node, case) pair of this launch is done
+static __device__ __forceinline__ void opty_wait_ready(const OptyParams& p, int& all_ready) {
+  if (!all_ready) {
+    if ((threadIdx.x & 31) == 0) {
+      const unsigned long long need_ = (unsigned long long)p.epoch * OPTY_PRE_GROUPS * (unsigned long long)p.n_nodes;
+      while (opty_ld_acquire(p.ready) < need_) {
+      }
+    }
+    __syncwarp();
+    all_ready = 1;
+    // the rows were written through the generic proxy (by other SMs), the bulk copies read through the async proxy
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+  }
+}
+// a thread takes up to OPTY_PRE_ILP nodes at a time: their (long, serial) sine / cosine chains interleave
+#define OPTY_PRE_ILP 3
+#define OPTY_PRE_PHASE()                                                                                   \
+  {                                                                                                        \
+    const int pg_ = opty_slot % OPTY_PRE_GROUPS, ci_ = opty_slot / OPTY_PRE_GROUPS;                        \
+    const int nc_ = (OPTY_NSLOTS - pg_ + OPTY_PRE_GROUPS - 1) / OPTY_PRE_GROUPS;                           \
+    const int per_ = ((p.n_nodes + nc_ - 1) / nc_ + 31) & ~31;                                             \
+    const int b0_ = ci_ * per_, b1_ = min(p.n_nodes, b0_ + per_);                                          \
+    for (int base_ = b0_ + (int)threadIdx.x; base_ < b1_; base_ += OPTY_PRE_ILP * OPTY_THREADS) {          \
+      int nodes_[OPTY_PRE_ILP]; /* (a repeated node writes the same values again) */                        \
+      _Pragma("unroll") for (int u_ = 0; u_ < OPTY_PRE_ILP; ++u_)                                          \
+        nodes_[u_] = min(base_ + u_ * OPTY_THREADS, b1_ - 1);                                              \
+      opty_pre_case(p, nodes_, pg_);                                                                       \
+    }                                                                                                      \
+    __threadfence();                                                                                       \
+    __syncthreads();                                                                                       \
+    if (threadIdx.x == 0 && b1_ > b0_) atomicAdd(p.ready, (unsigned long long)(b1_ - b0_));                \
+  }
+#define OPTY_WAIT_READY(t) opty_wait_ready(p, opty_all_ready);
+#else
+#define OPTY_PRE_PHASE()
+// launched behind the pre-pass with programmatic stream serialisation: its results are visible from here
+// (no effect after an ordinary launch)
+#define OPTY_WAIT_READY(t)                                     \
+  if (!opty_all_ready) {                                       \
+    asm volatile("griddepcontrol.wait;" ::: "memory");         \
+    opty_all_ready = 1;                                        \
+  }
+#endif
+
+// measurement aid (debug_nostore bit 1): thread 0 prints when its block started, how long every item took
+#if OPTY_DEBUG_NOSTORE & 2
+static __device__ __forceinline__ unsigned long long opty_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define OPTY_TIMING_BEGIN()                     \
+  unsigned long long opty_t0 = opty_gtime();    \
+  unsigned long long opty_tl = opty_t0;         \
+  unsigned opty_dt[12];                         \
+  int opty_gi[12];                              \
+  for (int i_ = 0; i_ < 12; ++i_) { opty_dt[i_] = 0; opty_gi[i_] = -1; } \
+  unsigned opty_st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define OPTY_TIMING_STAMP(k) \
+  if ((k) < 8) opty_st[(k)] = (unsigned)(opty_gtime() - opty_t0);
+#define OPTY_TIMING_ITEM()                                           \
+  if (threadIdx.x == 0 && opty_it < 12) {                            \
+    const unsigned long long n_ = opty_gtime();                      \
+    opty_dt[opty_it] = (unsigned)(n_ - opty_tl);                     \
+    opty_gi[opty_it] = opty_g;                                       \
+    opty_tl = n_;                                                    \
+  }
+#define OPTY_TIMING_END()                                                                                         \
+  if (threadIdx.x == 0)                                                                                           \
+    printf("T slot %d t0 %llu total %llu items %u : %d %u | %d %u | %d %u | %d %u | %d %u | %d %u | %d %u | %d %u | %d %u | %d %u\n", \
+           opty_slot, opty_t0, opty_gtime() - opty_t0, opty_it, opty_gi[0], opty_dt[0], opty_gi[1], opty_dt[1],      \
+           opty_gi[2], opty_dt[2], opty_gi[3], opty_dt[3], opty_gi[4], opty_dt[4], opty_gi[5], opty_dt[5], opty_gi[6],    \
+           opty_dt[6], opty_gi[7], opty_dt[7], opty_gi[8], opty_dt[8], opty_gi[9], opty_dt[9]);                          \
+  if ((threadIdx.x & 31) == 0)                                                                                    \
+    printf("W slot %d warp %d stamps %u %u %u %u %u %u %u %u\n", opty_slot, threadIdx.x >> 5, opty_st[0], opty_st[1], \
+           opty_st[2], opty_st[3], opty_st[4], opty_st[5], opty_st[6], opty_st[7]);
+#else
+#define OPTY_TIMING_STAMP(k)
+#define OPTY_TIMING_BEGIN()
+#define OPTY_TIMING_ITEM()
+#define OPTY_TIMING_END()
+#endif
+
+// constant rows: the node-invariant column runs (values p.cvals, filled by the invariants kernel) are the
+// same bytes for every node.  The block keeps one copy in shared memory; every lane of the launch owns a few
+// nodes and sends each run to its node rows with one bulk copy (cp.async.bulk.global.shared::cta) -- the
+// copies drain in the background while the warps work on their items.  (Plain 16-byte stores were tried
+// first: 41 MB of them at the start of the launch stall every warp for 7-13 us on the full store queues,
+// profiles/r02s_*.)
+#if OPTY_NCRUNS > 0
+#define OPTY_SMEM_CONST_BYTES ((OPTY_NCONST * 8 + 127) / 128 * 128)
+static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
+#if OPTY_STORE_HINT
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+               "r"(opty_smem_u32(src)), "r"(bytes), "l"(OPTY_STORE_POLICY)
+               : "memory");
+#else
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(opty_smem_u32(src)),
+               "r"(bytes)
+               : "memory");
+#endif
+}
+#define OPTY_CONST_FILL()                                                                                      \
+  double* opty_cbuf = reinterpret_cast<double*>(opty_smem + OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES + 128); \
+  for (int i_ = threadIdx.x; i_ < OPTY_NCONST; i_ += OPTY_THREADS) opty_cbuf[i_] = p.cvals[i_];                \
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+// The tile stores of the items and these copies share the SM's one in-order TMA queue, and a warp has ONE
+// staging buffer: a tile store that queues behind a backlog of copies stalls the next item until it has been
+// read.  The memory system on the other hand is the bottleneck of the whole launch (81 MB at ~4.5 TB/s) and
+// must not idle while the blocks wait for the pre-pass and work on their first items.  So a warp sends its
+// nodes in slices: OPTY_CONST_HEAD_PCT per cent when the block starts, OPTY_CONST_FIRST_PCT when its first
+// input window has arrived, OPTY_CONST_ITEM_PCT at the start of every later item (behind the tile store of
+// the item before), the rest after its last item.  Lanes 1..31 only while items follow: lane 0 waits on its
+// own store groups at every phase.
+#ifndef OPTY_CONST_HEAD_PCT
+#define OPTY_CONST_HEAD_PCT 25
+#endif
+#ifndef OPTY_CONST_FIRST_PCT
+#define OPTY_CONST_FIRST_PCT 35
+#endif
+#ifndef OPTY_CONST_ITEM_PCT
+#define OPTY_CONST_ITEM_PCT 15
+#endif
+#define OPTY_CONST_INIT()                                                                              \
+  const int opty_cnpw = (p.n_nodes + OPTY_NSLOTS * OPTY_WARPS - 1) / (OPTY_NSLOTS * OPTY_WARPS);       \
+  int opty_cn = (opty_slot * OPTY_WARPS + (int)(threadIdx.x >> 5)) * opty_cnpw;                        \
+  const int opty_ce = min(p.n_nodes, opty_cn + opty_cnpw);
+// the next `pct` per cent of the warp's nodes (everything that is left if `all`)
+#define OPTY_CONST_SLICE(pct, all)                                                                     \
+  if ((OPTY_DEBUG_NOSTORE & 1) == 0 && opty_cn < opty_ce) {                                            \
+    const int n1_ = (all) ? opty_ce : min(opty_ce, opty_cn + (opty_cnpw * (pct) + 99) / 100);          \
+    const int l_ = (threadIdx.x & 31) - ((all) ? 0 : 1), nl_ = (all) ? 32 : 31;                        \
+    if (l_ >= 0)                                                                                       \
+      for (int n_ = opty_cn + l_; n_ < n1_; n_ += nl_)                                                 \
+        for (int r_ = 0; r_ < OPTY_NCRUNS; ++r_)                                                       \
+          opty_bulk_store_1d(p.jac + (long long)n_ * OPTY_K + opty_crun[r_][0], opty_cbuf + opty_crun[r_][2], \
+                             (uint32_t)opty_crun[r_][1] * 16u);                                        \
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");                                          \
+    opty_cn = n1_;                                                                                     \
+  }
+#else
+#define OPTY_SMEM_CONST_BYTES 0
+#define OPTY_CONST_FILL()
+#define OPTY_CONST_INIT()
+#define OPTY_CONST_SLICE(pct, all)
+#endif
+
+#define OPTY_KERNEL_BEGIN()                                                                              \
+  OPTY_SMEM_SETUP()                                                                                      \
+  /* slot = block: with one block per SM and an otherwise idle device the hardware deals the blocks of   \
+     every launch out to the SMs in the same order, which is what keeps a body in the same instruction   \
+     caches from launch to launch; nothing depends on it but speed */                                     \
+  const int opty_slot = blockIdx.x;                                                                      \
+  if (threadIdx.x == 0) {                                                                                \
+    opty_mbar_init(&bar[0], 1);                                                                          \
+    opty_mbar_init(&bar[1], 1);                                                                          \
+  }                                                                                                      \
+  OPTY_CONST_FILL()                                                                                      \
+  __syncthreads();                                                                                       \
+  const int opty_seg_end = opty_sched_slot[opty_slot + 1];                                               \
+  int opty_seg = opty_sched_slot[opty_slot];                                                             \
+  int4 opty_sg = opty_sched_seg[opty_seg < opty_seg_end ? opty_seg : 0];                                 \
+  int opty_k = 0;                                                                                        \
+  unsigned opty_it = 0;                                                                                  \
+  int opty_flip = 0;                                                                                     \
+  int opty_all_ready = 0;                                                                                \
+  (void)opty_all_ready;                                                                                  \
+  OPTY_TIMING_BEGIN()                                                                                    \
+  OPTY_PRE_PHASE()                                                                                       \
+  /* the first part of the constant runs leaves while the block waits for the pre-pass */                \
+  OPTY_CONST_INIT()                                                                                      \
+  OPTY_CONST_SLICE(OPTY_CONST_HEAD_PCT, false)                                                           \
+  if (opty_seg < opty_seg_end && threadIdx.x < 32) {                                                     \
+    OPTY_WAIT_READY(opty_sg.y)                                                                           \
+    opty_issue_input(p, opty_sg, opty_sg.y, xin_bytes, &bar[0]);                                         \
+  }                                                                                                      \
+  OPTY_TIMING_STAMP(0)                                                                                   \
+  while (opty_seg < opty_seg_end) {                                                                      \
+    const int opty_g = opty_sg.x;                                                                        \
+    const int tile_node0 = (opty_sg.y + opty_k) * OPTY_THREADS;                                          \
+    int opty_nseg = opty_seg, opty_nk = opty_k + 1;                                                      \
+    int4 opty_nsg = opty_sg;                                                                             \
+    if (opty_nk >= opty_sg.z) {                                                                          \
+      ++opty_nseg;                                                                                       \
+      opty_nk = 0;                                                                                       \
+      if (opty_nseg < opty_seg_end) opty_nsg = opty_sched_seg[opty_nseg];                                \
+    }                                                                                                    \
+    /* the other buffer was handed back by the __syncthreads that ended the previous item */             \
+    if (opty_nseg < opty_seg_end && threadIdx.x < 32) {                                                  \
+      OPTY_WAIT_READY(opty_nsg.y + opty_nk)                                                              \
+      opty_issue_input(p, opty_nsg, opty_nsg.y + opty_nk, xin_bytes + ((opty_it + 1) & 1) * OPTY_XBUF_BYTES, \
+                       &bar[(opty_it + 1) & 1]);                                                         \
+    }                                                                                                    \
+    opty_mbar_wait(&bar[opty_it & 1], (opty_it >> 1) & 1);                                               \
+    if (opty_it == 0) {                                                                                  \
+      OPTY_CONST_SLICE(OPTY_CONST_FIRST_PCT, false)                                                      \
+    } else {                                                                                             \
+      OPTY_CONST_SLICE(OPTY_CONST_ITEM_PCT, false)                                                       \
+    }                                                                                                    \
+    OPTY_TIMING_STAMP(1 + 2 * opty_it)                                                                   \
+    OptyCtx ctx;                                                                                         \
+    ctx.lane = threadIdx.x & 31;                                                                         \
+    ctx.n_nodes = p.n_nodes;                                                                             \
+    ctx.ldt = p.ldt;                                                                                     \
+    ctx.xp = reinterpret_cast<const double*>(xin_bytes + (opty_it & 1) * OPTY_XBUF_BYTES +               \
+                                             (threadIdx.x / OPTY_XSEG) * OPTY_PXSEG_BYTES) +             \
+             (threadIdx.x % OPTY_XSEG);                                                                  \
+    ctx.xs = opty_smem_u32(ctx.xp);                                                                      \
+    ctx.ldc = p.ldc;                                                                                     \
+    ctx.tile0 = tiles + ((threadIdx.x >> 5) * OPTY_NBUF + (OPTY_NBUF == 2 ? opty_flip : 0)) * OPTY_TILE_DOUBLES;     \
+    ctx.tile1 = tiles + ((threadIdx.x >> 5) * OPTY_NBUF + (OPTY_NBUF == 2 ? 1 - opty_flip : 0)) * OPTY_TILE_DOUBLES; \
+    ctx.jac = p.jac;                                                                                     \
+    ctx.tm = &tm;                                                                                        \
+    ctx.node = tile_node0 + (threadIdx.x & ~31);                                                         \
+    ctx.active = (tile_node0 + (int)threadIdx.x) < p.n_nodes;                                            \
+    ctx.con = p.con + tile_node0 + threadIdx.x;                                                          \
+    if (ctx.node < p.n_nodes) {
+
+#define OPTY_KERNEL_END()                                                                              \
+    }                                                                                                  \
+    OPTY_TIMING_STAMP(2 + 2 * opty_it)                                                                 \
+    opty_flip ^= opty_group_odd[opty_g];                                                               \
+    __syncthreads();                                                                                   \
+    OPTY_TIMING_ITEM()                                                                                 \
+    opty_seg = opty_nseg;                                                                              \
+    opty_k = opty_nk;                                                                                  \
+    opty_sg = opty_nsg;                                                                                \
+    ++opty_it;                                                                                         \
+  }                                                                                                    \
+  OPTY_CONST_SLICE(100, true)                                                                                \
+  /* shared memory must outlive the tile stores that still read it */                                  \
+  if (OPTY_TMA_STORE) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");                   \
+  OPTY_TIMING_END()
 
 #else
 // Persistent, code-stationary kernel: grid = (resident blocks per SM) x SMs.
@@ -477,7 +821,9 @@ static __device__ __noinline__ int2 opty_steal(const OptyParams& p, const int* o
                 (long long)OPTY_R * OPTY_TW + node % OPTY_THREADS;
 #else
 #define OPTY_DRV(d, val) drv[(long long)(d) * p.ldt] = (val)
+#define OPTY_PCON(j, val) p.con[(long long)(j) * p.ldc + node] = (val)
 #define OPTY_PRE_BEGIN()                                        \
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
   const int node = blockIdx.x * OPTY_PRE_THREADS + threadIdx.x; \
   if (node >= p.n_nodes) return;                                \
   const double* xg = p.traj + node;                             \

@@ -14,5 +14,10 @@ struct OptyParams {
   int n_nodes;    // constraint nodes in this launch (N - 1 or a shard of them)
   int n_cols;     // valid trajectory columns (n_nodes + 1)
   int n_tiles;    // node tiles of 32*W nodes (persistent kernel)
-  int* work;      // persistent kernel: next tile per group [groups of the module] + departure counter
+  int* work;      // persistent kernel: next tile per group [groups of the module] + departure counter;
+                  // row-stationary kernel: launch number that last claimed each slot [slots]
+  int epoch;      // row-stationary kernel: number of this launch on the handle (1, 2, ...)
+  const double* cvals;  // row-stationary kernel: values of the constant column runs (tail of the invariants table)
+  unsigned long long* ready;  // row-stationary kernel with fused pre-pass: (node, case) pairs done per node tile
+                              // [n_tiles] and in total [1], summed over all launches of the handle
 };

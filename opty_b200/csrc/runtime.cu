@@ -64,6 +64,7 @@ struct DriverApi {
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                            unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
   CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -96,6 +97,7 @@ int init_driver() {
   if ((rc = load_entry("cuModuleGetGlobal", &g_drv.ModuleGetGlobal))) return rc;
   if ((rc = load_entry("cuFuncSetAttribute", &g_drv.FuncSetAttribute))) return rc;
   if ((rc = load_entry("cuLaunchKernel", &g_drv.LaunchKernel))) return rc;
+  if ((rc = load_entry("cuLaunchKernelEx", &g_drv.LaunchKernelEx))) return rc;
   if ((rc = load_entry("cuGetErrorString", &g_drv.GetErrorString))) return rc;
   if ((rc = load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", &g_drv.OccupancyMaxActiveBlocksPerMultiprocessor)))
     return rc;
@@ -236,11 +238,18 @@ enum {
   INFO_M = 21,
   INFO_P = 22,
   INFO_HAS_AUX = 23,
-  INFO_PERSISTENT = 24,
+  INFO_PERSISTENT = 24,  // 0 grid kernel, 1 code-stationary work queue, 2 row-stationary static schedule
+  INFO_MIN_BLOCKS = 25,
+  INFO_SMEM_BYTES = 26,  // row-stationary kernel: dynamic shared memory per block
+  INFO_SLOTS = 27,       //   blocks to launch (one per slot of the emitted schedule)
+  INFO_TILES = 28,       //   node tiles the schedule was laid out for
+  INFO_CVAL0 = 29,       //   first entry of the invariants table that belongs to the constant column runs
+  INFO_FUSED_PRE = 30,   //   1: the main kernel does the pre-pass's work itself (no pre-pass launch)
+  INFO_XROWS = 31,       //   rows of the input window a block fetches per item (box height of the input map)
   INFO_WORDS = 32
 };
 const int kInfoMagic = 0x4f505459;
-const int kEmitterVersion = 6;
+const int kEmitterVersion = 7;
 const int kMaxMaps = 8;
 
 }  // namespace
@@ -258,7 +267,7 @@ struct opty_colloc {
 
   // kernel geometry, read from the primary module
   int warps = 0, num_derived = 0, pre_groups = 0, tma_load = 0, tma_store = 0, tile_bufs = 0,
-      tile_doubles = 0, num_inv = 0, persistent = 0;
+      tile_doubles = 0, num_inv = 0, persistent = 0, stat_smem = 0, stat_slots = 0, stat_tiles = 0, stat_cval0 = 0, fused_pre = 0, stat_xrows = 0;
 
   struct Module {
     CUmodule mod = nullptr;
@@ -269,6 +278,7 @@ struct opty_colloc {
     int widths[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<std::vector<unsigned char>> tmaps;  // per ring slot: OptyTmaps blob (in + out[nmaps])
     int* d_work = nullptr;      // persistent kernel: tile counter per group + departure counter
+    unsigned long long* d_ready = nullptr;  // row-stationary kernel: progress counters of the fused pre-pass
     unsigned persist_grid = 0;  // resident blocks on the whole device
   };
   std::vector<Module> modules;  // [0] = primary (carries opty_colloc_inv / opty_colloc_pre)
@@ -347,8 +357,9 @@ int build_tmaps(opty_colloc* h, opty_colloc::Module& m, int slot) {
   if (h->tma_load == 1) {
     const uint32_t threads = 32u * h->warps;
     const uint32_t xbox = (threads <= 128u ? threads : 128u) + 2u;
-    if ((rc = encode_2d(&maps[0], h->d_traj, (uint64_t)h->ncols, (uint64_t)h->RD, (uint64_t)h->ldt * 8, xbox,
-                        (uint32_t)h->RD)))
+    // (row-stationary kernel: a window of the rows, the height of the largest one any group reads)
+    const uint32_t xrows = h->persistent == 2 ? (uint32_t)h->stat_xrows : (uint32_t)h->RD;
+    if ((rc = encode_2d(&maps[0], h->d_traj, (uint64_t)h->ncols, (uint64_t)h->RD, (uint64_t)h->ldt * 8, xbox, xrows)))
       return rc;
   }
   if (h->tma_store) {
@@ -397,6 +408,15 @@ int load_module(opty_colloc* h, const void* cubin, bool primary) {
     h->tile_doubles = info[INFO_TILE_DOUBLES];
     h->num_inv = info[INFO_NUM_INV];
     h->persistent = info[INFO_PERSISTENT];
+    h->stat_smem = info[INFO_SMEM_BYTES];
+    h->stat_slots = info[INFO_SLOTS];
+    h->stat_tiles = info[INFO_TILES];
+    h->stat_cval0 = info[INFO_CVAL0];
+    h->fused_pre = info[INFO_FUSED_PRE];
+    h->stat_xrows = info[INFO_XROWS];
+    if (h->persistent == 2 && (h->stat_smem < 1 || h->stat_slots < 1 || h->stat_tiles < 1 || h->stat_xrows < 1 ||
+                               h->stat_xrows > 256))
+      return bail(fail(OPTY_ERR_ARG, "invalid row-stationary geometry in the module info table"));
     if (h->warps < 1 || h->warps > 32 || h->tile_bufs < 1 || h->tile_bufs > 2 || h->tile_doubles < 64 ||
         h->num_derived < 0 || (h->num_derived > 0 && h->pre_groups < 1))
       return bail(fail(OPTY_ERR_ARG, "invalid kernel geometry in the module info table"));
@@ -437,7 +457,15 @@ int finish_module(opty_colloc* h, opty_colloc::Module& m) {
     int rc = build_tmaps(h, m, s);
     if (rc) return rc;
   }
-  if (h->persistent) {
+  if (h->persistent == 2) {
+    // one block per slot of the schedule the emitter laid out; `d_work` holds the launch number that last
+    // claimed each slot
+    m.persist_grid = (unsigned)h->stat_slots;
+    RT_CHECK(cudaMalloc(&m.d_work, (size_t)h->stat_slots * sizeof(int)));
+    RT_CHECK(cudaMemset(m.d_work, 0, (size_t)h->stat_slots * sizeof(int)));
+    RT_CHECK(cudaMalloc(&m.d_ready, (size_t)(h->stat_tiles + 1) * sizeof(unsigned long long)));
+    RT_CHECK(cudaMemset(m.d_ready, 0, (size_t)(h->stat_tiles + 1) * sizeof(unsigned long long)));
+  } else if (h->persistent) {
     // as many blocks as fit on the device at once: every block loops over node tiles
     int per_sm = 0;
     DRV_CHECK(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m.f_eval, 32 * h->warps, h->smem_bytes));
@@ -491,12 +519,17 @@ int launch_eval(opty_colloc* h, bool record_events = false) {
   p.n_cols = h->ncols;
   p.n_tiles = (int)h->grid_x;
   p.work = nullptr;
+  p.ready = nullptr;
+  p.epoch = (int)(h->eval_seq & 0x7fffffff);  // launches of this handle so far, this one included
+  p.cvals = h->d_inv + h->stat_cval0;
+  bool pre_launched = false;
   {
     // pre-pass: derived rows, and for direct-input modules the tile-by-tile copy of the trajectory rows
     // (chunks of 16 rows in grid.y behind the groups of derived rows)
     const unsigned copy_groups = h->tma_load == 2 ? (unsigned)((h->R + 15) / 16) : 0u;
-    const unsigned gy = (h->num_derived > 0 ? (unsigned)h->pre_groups : 0u) + copy_groups;
-    if (gy > 0) {
+    const unsigned gy = (unsigned)h->pre_groups + copy_groups;
+    if (gy > 0 && !h->fused_pre) {
+      pre_launched = getenv("OPTY_B200_NO_PDL") == nullptr;
       void* pargs[1] = {&p};
       DRV_CHECK(g_drv.LaunchKernel(h->f_pre, (unsigned)((h->nn + 1 + 127) / 128), gy, 1, 128, 1, 1, 0,
                                    (CUstream)h->stream, pargs, nullptr));
@@ -505,8 +538,27 @@ int launch_eval(opty_colloc* h, bool record_events = false) {
   }
   for (auto& m : h->modules) {
     p.work = m.d_work;
+    p.ready = m.d_ready;
     void* args[2] = {m.tmaps[h->ring].data(), &p};
-    if (h->persistent) {
+    if (h->persistent == 2 && pre_launched) {
+      // row-stationary kernel behind the pre-pass: programmatic dependent launch -- its blocks set themselves
+      // up while the pre-pass drains and wait (griddepcontrol.wait) before they fetch their first input rows
+      CUlaunchConfig lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDimX = m.persist_grid;
+      lc.gridDimY = lc.gridDimZ = 1;
+      lc.blockDimX = 32u * h->warps;
+      lc.blockDimY = lc.blockDimZ = 1;
+      lc.sharedMemBytes = h->smem_bytes;
+      lc.hStream = (CUstream)h->stream;
+      CUlaunchAttribute attr;
+      memset(&attr, 0, sizeof(attr));
+      attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+      attr.value.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = &attr;
+      lc.numAttrs = 1;
+      DRV_CHECK(g_drv.LaunchKernelEx(&lc, m.f_eval, args, nullptr));
+    } else if (h->persistent) {
       // code-stationary persistent kernel: resident blocks pull (group, tile) work items
       DRV_CHECK(g_drv.LaunchKernel(m.f_eval, m.persist_grid, 1, 1, 32u * h->warps, 1, 1, h->smem_bytes,
                                    (CUstream)h->stream, args, nullptr));
@@ -715,8 +767,11 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   CREATE_RT(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
   CREATE_RT(cudaEventCreateWithFlags(&h->ev_con, cudaEventDisableTiming));
 
-  CREATE_RT(cudaMalloc(&h->d_traj, (size_t)h->RD * h->ldt * 8));
-  CREATE_RT(cudaMemsetAsync(h->d_traj, 0, (size_t)h->RD * h->ldt * 8, h->stream));
+  // (+ one input row of the widest block: the row-stationary kernel's bulk copies fetch whole rows of
+  // 32*W + 2 columns, the last tile's reach past the valid columns)
+  const size_t traj_bytes = (size_t)h->RD * h->ldt * 8 + (32 * 32 + 2) * 8;
+  CREATE_RT(cudaMalloc(&h->d_traj, traj_bytes));
+  CREATE_RT(cudaMemsetAsync(h->d_traj, 0, traj_bytes, h->stream));
   const int nuni = cfg->pk + cfg->r + 1;
   CREATE_RT(cudaMalloc(&h->d_uni, (size_t)nuni * 8));
   CREATE_RT(cudaMemsetAsync(h->d_uni, 0, (size_t)nuni * 8, h->stream));
@@ -744,6 +799,7 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   const unsigned xin_bytes =
       h->tma_load == 2 ? 0u : nseg * (unsigned)round_up((int64_t)h->RD * (xseg + 2u) * 8, 128);
   h->smem_bytes = tiles_bytes + xin_bytes + 128u;
+  if (h->persistent == 2) h->smem_bytes = (unsigned)h->stat_smem;
   if (const char* pad = getenv("OPTY_B200_DEBUG_SMEM_FLOOR")) {
     // measurement aid: a larger dynamic shared-memory request caps the resident blocks per SM
     const unsigned floor_bytes = (unsigned)atoi(pad);
@@ -756,6 +812,10 @@ int opty_colloc_create(const opty_colloc_cfg* cfg, const void* cubin, size_t cub
   CREATE_CHECK(finish_module(h, h->modules[0]));
 
   h->grid_x = (unsigned)((h->nn + 32 * h->warps - 1) / (32 * h->warps));
+  if (h->persistent == 2 && (int)h->grid_x != h->stat_tiles) {
+    opty_colloc_destroy(h);
+    return fail(OPTY_ERR_ARG, "the module's static schedule was laid out for a different number of nodes");
+  }
   if (h->tma_load == 2) {
     const size_t tiled_bytes = (size_t)h->grid_x * h->RD * (32 * h->warps + 2) * 8;
     CREATE_RT(cudaMalloc(&h->d_tiled, tiled_bytes));
@@ -793,6 +853,7 @@ int opty_colloc_destroy(opty_colloc_t* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   for (auto& m : h->modules) {
     cudaFree(m.d_work);
+    cudaFree(m.d_ready);
     if (m.mod && g_drv.ModuleUnload) g_drv.ModuleUnload(m.mod);
   }
   delete h;

@@ -70,11 +70,17 @@ DEFAULT_CUDA_OPTIONS = {
                                 # shared memory, False = plain loads into
                                 # shared memory, 'direct' = no staging
     'tma_store': True,
-    'persistent': False,        # code-stationary persistent main kernel: the
-                                # resident blocks of an SM keep one group for
-                                # as long as it has node tiles left (the body
-                                # stays in the instruction cache) and pull
-                                # tiles from per-group atomic counters
+    'persistent': 'auto',       # 'auto': 'stationary' where it applies (below),
+                                # else the grid kernel (False).
+                                # True: code-stationary persistent main kernel:
+                                # the resident blocks of an SM keep one group
+                                # for as long as it has node tiles left (the
+                                # body stays in the instruction cache) and pull
+                                # tiles from per-group atomic counters.
+                                # 'stationary': one block per SM, one equation
+                                # row per group, static schedule that keeps a
+                                # row on the same SMs, next item's input
+                                # prefetched (csrc/colloc_kernel.cuh)
     'pre_pass': True,           # shared expensive sub-expressions once per node
     'schedule': 'auto',         # register-pressure scheduler (schedule.py):
                                 # 'auto' = for groups whose plain order keeps
@@ -96,6 +102,25 @@ DEFAULT_CUDA_OPTIONS = {
     'out_ring': 2,              # device output sets to rotate through (2: an
                                 # evaluation at a new point does not wait for
                                 # the speculative Jacobian copy of the last one)
+    'const_rows': True,         # row-stationary kernel: equations whose
+                                # partials are all node-invariant are written
+                                # as constant column runs, not as groups
+    'fused_pre': False,         # row-stationary kernel: derived rows and the
+                                # residuals of constant rows as phase 0 of
+                                # the main kernel instead of a pre-pass launch
+                                # (slower: 256 threads per SM cannot hide the
+                                # latency of the sine / cosine chains,
+                                # profiles/r02y_*)
+    'item_cost': 16000,         # row-stationary schedule: fixed cost of an item
+                                # in units of 1/20 operation
+    'store_hint': 1,            # L2 policy of the Jacobian stores: 0 default,
+                                # 1 evict_first (the output is read by nobody
+                                # on the device; code and trajectory stay in
+                                # L2), 2 evict_last
+    'const_head_pct': (25, 35, 15),  # per cent of its constant runs a warp
+                                # sends when the block starts / when its first
+                                # input has arrived / with every later item
+                                # (the rest after its last item)
     'use_sympy_cse': True,
     'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
     'prefetch_jacobian': True,  # constraints() starts the Jacobian D2H early
@@ -636,7 +661,35 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     """Groups, emits and compiles the CUDA module of a
     :class:`CollocationProgram` for ``num_nodes`` evaluation nodes.  Needs nvcc
     but no GPU.  Returns ``(parts, derived, source, meta, cubin, cubin_path,
-    cache_hit)``."""
+    cache_hit)``.
+
+    ``persistent='auto'`` picks the row-stationary kernel for collocation
+    programs whose equations have an even number of partials and whose input
+    windows fit next to the staging buffers of an 8-warp block in shared
+    memory (up to ~30 trajectory + derived rows: the 10-link pendulum), the
+    grid kernel otherwise."""
+    if opts['persistent'] == 'auto':
+        eligible = (pair is not None and prog.P % 2 == 0 and
+                    bool(opts['tma_store']) and opts['tma_load'] is True and
+                    opts['groups'] == 'auto' and
+                    opts['warps_per_block'] == 'auto' and
+                    opts['compile_shards'] in ('auto', 1) and
+                    prog.stats()['varying_cost'] < 40000)
+        if eligible:
+            try:
+                return _prepare_program_module(
+                    prog, num_nodes, method,
+                    dict(opts, persistent='stationary', tile_bufs=1),
+                    tmp_dir, show_compile_output, pair)
+            except ValueError as err:
+                logger.info('Row-stationary kernel not used: %s', err)
+        opts = dict(opts, persistent=False)
+    return _prepare_program_module(prog, num_nodes, method, opts, tmp_dir,
+                                   show_compile_output, pair)
+
+
+def _prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
+                            show_compile_output=False, pair=None):
     M = prog.M
     K = M * prog.P
     tma_store = bool(opts['tma_store']) and K % 2 == 0
@@ -644,7 +697,10 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         tma_load = 2
     else:
         tma_load = int(bool(opts['tma_load']) and prog.R <= 256)
+    stationary = opts['persistent'] in ('stationary', 2)
     groups = opts['groups']
+    if stationary and groups == 'auto':
+        groups = M
     if groups == 'auto':
         node_warps = -(-num_nodes // 32)
         g_par = -(-int(opts['target_warps']) // node_warps)
@@ -662,7 +718,20 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         0, unit_rows * prog.P, tile_cols, pair if unit_rows == 1 else None,
         tma_store))
 
+    const_rows = []
+    if stationary and opts['const_rows'] and unit_rows == 1 and tma_store:
+        kinds = prog.entry_kind()
+        const_rows = [j for j in range(M)
+                      if max(kinds[j * prog.P:(j + 1) * prog.P]) < 2]
+        if len(const_rows) == M:
+            const_rows = const_rows[1:]     # the main kernel needs a group
+
     def column_parts(stop=None):
+        if stationary and groups >= M // unit_rows:
+            # one equation row (two when P is odd) per group
+            rows = [(r, min(M, r + unit_rows)) for r in range(0, M, unit_rows)
+                    if r not in const_rows]
+            return [(r0 * prog.P, r1 * prog.P) for r0, r1 in rows]
         rows = prog.partition_rows(groups, col_align=align, stop=stop)
         if opts['groups'] == 'auto':
             # A warp has one tile store in flight per staging buffer, so a
@@ -698,8 +767,13 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     if wpb == 'auto':
         node_warps = -(-num_nodes // 32)
         wpb = 8 if node_warps * len(parts) >= 8 * 148 * 6 else 2
+        if stationary:
+            wpb = 8
     wpb = int(wpb)
     mbs = opts['min_blocks_per_sm']
+    if stationary:
+        mbs = 1 if mbs == 'auto' else int(mbs)
+        tma_load = 1
     if mbs == 'auto':
         # plain-order bodies need the whole register file of 8 warps
         light = opts['schedule'] is False or (
@@ -708,7 +782,7 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         mbs = max(1, (8 if light else 16) // wpb)
     mbs = int(mbs)
     tile_bufs = int(opts['tile_bufs'])
-    if tma_load != 2:
+    if tma_load != 2 and not stationary:
         # staged input must fit beside the staging buffers in 227 KB of
         # shared memory per block; otherwise the lanes read the trajectory
         # matrix directly (coalesced, read-only path)
@@ -728,7 +802,11 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         tile_cols=tile_cols, warps_per_block=wpb, min_blocks_per_sm=mbs,
         tma_load=tma_load, tma_store=tma_store, derived=derived,
         debug_nostore=opts['debug_nostore'], tile_bufs=tile_bufs, pair=pair,
-        persistent=bool(opts['persistent']),
+        persistent=2 if stationary else int(bool(opts['persistent'])),
+        num_nodes=num_nodes, blocks_per_sm=mbs if stationary else 1,
+        const_rows=const_rows, const_head_pct=opts['const_head_pct'],
+        store_hint=opts['store_hint'], fused_pre=opts['fused_pre'],
+        item_cost=opts['item_cost'],
         schedule_options=sched_opts,
         workers=(os.cpu_count() or 1) if cost >= 20000 else 1)
 
@@ -738,6 +816,8 @@ def prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
     # function serially (opty/utils.py:866-907); at the 50-link chain that is
     # the dominant set-up cost.
     shards = opts['compile_shards']
+    if stationary:
+        shards = 1
     if shards == 'auto':
         big = cost >= 40000 and len(parts) >= 4
         shards = min(len(parts), os.cpu_count() or 1, 16) if big else 1
@@ -1103,10 +1183,18 @@ class _MultiDeviceEvaluator(object):
                 # (the automatic geometry depends on the shard size; sums
                 # accumulated in a different order would differ in the last
                 # bit between neighbouring shards)
-                part._cuda_options = dict(
-                    part._cuda_options, groups=len(first.parts),
-                    warps_per_block=first.meta['warps_per_block'],
-                    min_blocks_per_sm=first.meta['min_blocks_per_sm'])
+                if first.meta['persistent'] == 2:
+                    # (row-stationary kernel: one equation per group anyway)
+                    part._cuda_options = dict(
+                        part._cuda_options, persistent='stationary',
+                        tile_bufs=first.meta['tile_bufs'],
+                        warps_per_block=first.meta['warps_per_block'])
+                else:
+                    part._cuda_options = dict(
+                        part._cuda_options, groups=len(first.parts),
+                        persistent=bool(first.meta['persistent']),
+                        warps_per_block=first.meta['warps_per_block'],
+                        min_blocks_per_sm=first.meta['min_blocks_per_sm'])
             ev = _CudaEvaluator(part)
             self.evaluators.append(ev)
             first = first or ev

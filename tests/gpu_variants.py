@@ -27,6 +27,16 @@ CONFIG2_VARIANTS = [
     {'persistent': True, 'groups': 11},
     {'persistent': True, 'groups': 6, 'tma_load': 'direct',
      'compile_shards': 2, 'tile_bufs': 2},
+    # the grid kernel with automatic grouping (the default is the
+    # row-stationary kernel at this problem)
+    {'persistent': False},
+    # row-stationary kernel: narrow tiles in two staging buffers (an item has
+    # an odd number of phases: the buffers swap), the pre-pass fused into the
+    # main kernel, constant rows as ordinary groups, plain input loads
+    {'persistent': 'stationary', 'tile_bufs': 2, 'tile_cols': 22},
+    {'persistent': 'stationary', 'tile_bufs': 1, 'fused_pre': True},
+    {'persistent': 'stationary', 'tile_bufs': 1, 'const_rows': False,
+     'warps_per_block': 4, 'store_hint': 0},
 ]
 BITWISE = {'fmad': False, 'reassociate': False}
 

@@ -26,7 +26,8 @@ def main():
     for name, opts in VARIANTS:
         opts = dict(opts)
         for key in ('OPTY_B200_REPL_ROWS', 'OPTY_B200_REPL_TILES',
-                    'OPTY_B200_REPL_MODE', 'OPTY_B200_REPL_NODES'):
+                    'OPTY_B200_REPL_MODE', 'OPTY_B200_REPL_NODES',
+                    'OPTY_B200_NO_PDL'):
             os.environ.pop(key, None)
         for key, val in opts.pop('env', {}).items():
             os.environ[key] = str(val)
