@@ -470,7 +470,7 @@ class _ScheduledWriter(object):
 _INPUT_REF = __import__('re').compile(r'\bX([ABD])\((\d+)\)')
 
 
-def stationary_schedule(costs, n_tiles, n_slots):
+def stationary_schedule(costs, n_tiles, n_slots, strided=True):
     """Static work assignment of the row-stationary kernel.  ``costs[g]`` is
     the estimated time of one item (one node tile of a block x group ``g``);
     every group has ``n_tiles`` items.  Returns one list of segments
@@ -489,21 +489,44 @@ def stationary_schedule(costs, n_tiles, n_slots):
     heavy = [g for g in range(G) if costs[g] >= 0.25 * cmax]
     light = [g for g in range(G) if costs[g] < 0.25 * cmax]
     heavy.sort(key=lambda g: -costs[g])
-    total_heavy = float(sum(costs[g] for g in heavy) * n_tiles) or 1.0
-    per_slot = total_heavy / n_slots
     load = [0.0] * n_slots
     hv = [[] for _ in range(n_slots)]
-    cum = 0.0
-    for g in heavy:
-        for t in range(n_tiles):
-            s = min(n_slots - 1, int((cum + 0.5 * costs[g]) / per_slot))
-            cum += costs[g]
-            load[s] += costs[g]
-            if hv[s] and hv[s][-1][0] == g and \
-                    hv[s][-1][1] + hv[s][-1][2] == t:
-                hv[s][-1][2] += 1
-            else:
-                hv[s].append([g, t, 1])
+    if strided and 0 < len(heavy) <= n_slots:
+        # whole slots per group (one more slot to the group whose busiest
+        # slot is the busiest, until none is left), tile t of a group on the
+        # group's slot t mod S, in step t div S: every group then walks the
+        # node tiles at the same pace, and the pieces of a node's Jacobian
+        # row reach memory within about one item time of each other -- the
+        # store stream is 15-20 % faster that way (tools/write_path_bench.cu,
+        # variants I/J/K)
+        S = {g: 1 for g in heavy}
+        worst = [(-(-(-n_tiles // S[g])) * costs[g], g) for g in heavy]
+        heapq.heapify(worst)
+        for _ in range(n_slots - len(heavy)):
+            _, g = heapq.heappop(worst)
+            S[g] += 1
+            heapq.heappush(worst, (-(-(-n_tiles // S[g])) * costs[g], g))
+        base = 0
+        for g in heavy:
+            for t in range(n_tiles):
+                s_ = base + t % S[g]
+                hv[s_].append([g, t, 1])
+                load[s_] += costs[g]
+            base += S[g]
+    else:
+        total_heavy = float(sum(costs[g] for g in heavy) * n_tiles) or 1.0
+        per_slot = total_heavy / n_slots
+        cum = 0.0
+        for g in heavy:
+            for t in range(n_tiles):
+                s = min(n_slots - 1, int((cum + 0.5 * costs[g]) / per_slot))
+                cum += costs[g]
+                load[s] += costs[g]
+                if hv[s] and hv[s][-1][0] == g and \
+                        hv[s][-1][1] + hv[s][-1][2] == t:
+                    hv[s][-1][2] += 1
+                else:
+                    hv[s].append([g, t, 1])
     lt = [[] for _ in range(n_slots)]
     heap = [(load[s], s) for s in range(n_slots)]
     heapq.heapify(heap)
@@ -603,7 +626,7 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
                 schedule_options=None, workers=1, persistent=False,
                 num_sms=148, num_nodes=None, blocks_per_sm=1, const_rows=(),
                 const_head_pct=(25, 35, 15), store_hint=0, fused_pre=False,
-                item_cost=16000):
+                item_cost=16000, strided_schedule=True, const_pre_pct=0):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block,
     whole equations each; a group also owns the residuals of its rows).
@@ -707,7 +730,8 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         # placeholder, replaced once the bodies' input windows are known
         w('@@XROWS_MAX@@')
     w('#define OPTY_PRE_GROUPS {}'.format(
-        len(set(T.a[nid] for nid in derived)) + (1 if const_rows else 0)))
+        len(set(T.a[nid] for nid in derived)) + (1 if const_rows else 0) +
+        (8 if (const_rows and with_aux and int(const_pre_pct) > 0) else 0)))
     w('#define OPTY_NCRUNS {}'.format(len(const_runs)))
     w('#define OPTY_NCONST {}'.format(len(const_entries)))
     chead = list(const_head_pct) if isinstance(
@@ -751,8 +775,17 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         by_arg.setdefault(T.a[nid], []).append(k)
     for ks in by_arg.values():
         pre_chunks.append(ks)
-    pre_groups = len(pre_chunks) + (1 if const_rows else 0)
+    const_pre_pct = int(const_pre_pct) if (const_runs and with_aux) else 0
+    pre_groups = len(pre_chunks) + (1 if const_rows else 0) + \
+        (8 if const_pre_pct > 0 else 0)
     pre_ops = 0
+    if const_runs:
+        w('__device__ const int opty_crun[OPTY_NCRUNS][3] = {{{}}};'.format(
+            ', '.join('{{{}, {}, {}}}'.format(c0, n // 2, off)
+                      for c0, n, off in const_runs)))
+    if const_pre_pct > 0:
+        out.insert(out.index('#include "colloc_kernel.cuh"'),
+                   '#define OPTY_CONST_PRE_PCT {}'.format(const_pre_pct))
     fused_pre = bool(fused_pre) and stationary and with_aux and \
         0 < pre_groups <= num_sms * blocks_per_sm
     if fused_pre:
@@ -920,7 +953,8 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         # operation (profiles/r02z_*)
         costs = [20.0 * gm['ops'] + 43.0 * gm['ncols'] + float(item_cost)
                  for gm in group_meta]
-        sched = stationary_schedule(costs, n_tiles, n_slots)
+        sched = stationary_schedule(costs, n_tiles, n_slots,
+                                    strided=bool(strided_schedule))
         starts, segs = [0], []
         for slot in sched:
             segs.extend(slot)
@@ -928,10 +962,6 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         xrows_max = max(gm['xrows'] for gm in group_meta)
         out[out.index('@@XROWS_MAX@@')] = \
             '#define OPTY_XROWS_MAX {}'.format(xrows_max)
-        if const_runs:
-            w('__device__ const int opty_crun[OPTY_NCRUNS][3] = {{{}}};'.format(
-                ', '.join('{{{}, {}, {}}}'.format(c0, n // 2, off)
-                          for c0, n, off in const_runs)))
         w('__device__ const int opty_group_xrow0[OPTY_NGROUPS] = {{{}}};'.format(
             ', '.join(str(gm['xrow0']) for gm in group_meta)))
         w('__device__ const int opty_group_xrows[OPTY_NGROUPS] = {{{}}};'.format(

@@ -131,12 +131,14 @@ static __device__ __forceinline__ void opty_mbar_wait(uint64_t* bar, uint32_t pa
       : "memory");
 }
 
+// (input tiles are read by every group: evict_last keeps the few MB of the trajectory matrix in L2 beside
+// the output stream -- without the hint the row-stationary kernel re-read 20 MB of it from DRAM per launch)
 static __device__ __forceinline__ void opty_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
                                                         uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          opty_smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(opty_smem_u32(bar))
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+      "[%4], %5;" ::"r"(opty_smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(opty_smem_u32(bar)), "l"(0x14F0000000000000ull)
       : "memory");
 }
 
@@ -465,6 +467,12 @@ static __device__ __forceinline__ void opty_issue_input_rows(const CUtensorMap* 
 #ifndef OPTY_FUSED_PRE
 #define OPTY_FUSED_PRE 0
 #endif
+// the pre-pass kernel writes the constant runs of the first OPTY_CONST_PRE_PCT per cent of the nodes: the
+// memory system has nothing else to do while it runs
+#ifndef OPTY_CONST_PRE_PCT
+#define OPTY_CONST_PRE_PCT 0
+#endif
+#define OPTY_CONST_PRE_NODES(n) ((int)(((long long)(n) * OPTY_CONST_PRE_PCT) / 100))
 #if OPTY_FUSED_PRE
 static __device__ __forceinline__ unsigned long long opty_ld_acquire(const unsigned long long* a) {
   unsigned long long v;
@@ -595,8 +603,9 @@ static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void*
 #define OPTY_CONST_ITEM_PCT 15
 #endif
 #define OPTY_CONST_INIT()                                                                              \
-  const int opty_cnpw = (p.n_nodes + OPTY_NSLOTS * OPTY_WARPS - 1) / (OPTY_NSLOTS * OPTY_WARPS);       \
-  int opty_cn = (opty_slot * OPTY_WARPS + (int)(threadIdx.x >> 5)) * opty_cnpw;                        \
+  const int opty_cpre = OPTY_CONST_PRE_NODES(p.n_nodes); /* written by the pre-pass kernel */          \
+  const int opty_cnpw = (p.n_nodes - opty_cpre + OPTY_NSLOTS * OPTY_WARPS - 1) / (OPTY_NSLOTS * OPTY_WARPS); \
+  int opty_cn = opty_cpre + (opty_slot * OPTY_WARPS + (int)(threadIdx.x >> 5)) * opty_cnpw;            \
   const int opty_ce = min(p.n_nodes, opty_cn + opty_cnpw);
 // the next `pct` per cent of the warp's nodes (everything that is left if `all`)
 #define OPTY_CONST_SLICE(pct, all)                                                                     \
@@ -822,8 +831,31 @@ static __device__ __noinline__ int2 opty_steal(const OptyParams& p, const int* o
 #else
 #define OPTY_DRV(d, val) drv[(long long)(d) * p.ldt] = (val)
 #define OPTY_PCON(j, val) p.con[(long long)(j) * p.ldc + node] = (val)
+#if OPTY_PERSISTENT == 2 && OPTY_CONST_PRE_PCT > 0 && OPTY_NCRUNS > 0
+// last OPTY_PRE_CONST_SLICES slices of the grid: lanes = consecutive 16-byte pieces of a run, a warp = 4 nodes
+// (many warps with few stores each: a warp's stores leave one after the other)
+#define OPTY_PRE_CONST_SLICES 8
+#define OPTY_PRE_CONST_SLICE()                                                                          \
+  if (blockIdx.y >= OPTY_PRE_GROUPS - OPTY_PRE_CONST_SLICES) {                                          \
+    const int n0_ = blockIdx.x * OPTY_PRE_THREADS + (int)(threadIdx.x & ~31u) +                         \
+                    (int)(blockIdx.y - (OPTY_PRE_GROUPS - OPTY_PRE_CONST_SLICES)) * (32 / OPTY_PRE_CONST_SLICES); \
+    const int n1_ = min(OPTY_CONST_PRE_NODES(p.n_nodes), n0_ + 32 / OPTY_PRE_CONST_SLICES);             \
+    for (int r_ = 0; r_ < OPTY_NCRUNS; ++r_) {                                                          \
+      const double2* v_ = reinterpret_cast<const double2*>(p.cvals + opty_crun[r_][2]);                 \
+      for (int k_ = threadIdx.x & 31; k_ < opty_crun[r_][1]; k_ += 32) {                                \
+        const double2 v2_ = v_[k_];                                                                     \
+        double2* d_ = reinterpret_cast<double2*>(p.jac + (long long)n0_ * OPTY_K + opty_crun[r_][0]) + k_; \
+        for (int n_ = n0_; n_ < n1_; ++n_, d_ += OPTY_K / 2) __stcs(d_, v2_);                           \
+      }                                                                                                 \
+    }                                                                                                   \
+    return;                                                                                             \
+  }
+#else
+#define OPTY_PRE_CONST_SLICE()
+#endif
 #define OPTY_PRE_BEGIN()                                        \
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  OPTY_PRE_CONST_SLICE()                                        \
   const int node = blockIdx.x * OPTY_PRE_THREADS + threadIdx.x; \
   if (node >= p.n_nodes) return;                                \
   const double* xg = p.traj + node;                             \

@@ -111,6 +111,11 @@ DEFAULT_CUDA_OPTIONS = {
                                 # (slower: 256 threads per SM cannot hide the
                                 # latency of the sine / cosine chains,
                                 # profiles/r02y_*)
+    'const_pre_pct': 0,         # per cent of the nodes whose constant runs the
+                                # pre-pass kernel writes (plain stores)
+    'strided_schedule': True,   # row-stationary schedule: whole slots per
+                                # group, node tiles dealt round robin to them
+                                # (all groups walk the tiles at the same pace)
     'item_cost': 16000,         # row-stationary schedule: fixed cost of an item
                                 # in units of 1/20 operation
     'store_hint': 1,            # L2 policy of the Jacobian stores: 0 default,
@@ -807,6 +812,8 @@ def _prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         const_rows=const_rows, const_head_pct=opts['const_head_pct'],
         store_hint=opts['store_hint'], fused_pre=opts['fused_pre'],
         item_cost=opts['item_cost'],
+        strided_schedule=opts['strided_schedule'],
+        const_pre_pct=opts['const_pre_pct'],
         schedule_options=sched_opts,
         workers=(os.cpu_count() or 1) if cost >= 20000 else 1)
 

@@ -491,6 +491,84 @@ def test_sharded_modules_compile_for_sm100a_and_carry_their_geometry():
         assert regs <= 128 and 'LOCAL:0' in line
 
 
+def test_stationary_schedule_covers_every_item_once():
+    """Static work assignment of the row-stationary kernel: every (group, node
+    tile) item lands in exactly one slot, in both layouts; the strided layout
+    gives a group whole slots and walks its tiles round robin over them."""
+    from opty_b200.codegen import stationary_schedule
+    for costs, n_tiles, n_slots in (
+            ([29.0, 45.5, 45.1, 44.8, 44.1, 43.1, 41.8, 40.3, 38.0, 34.3,
+              31.5], 40, 148),
+            ([10.0, 1.0, 1.0, 9.0], 7, 5),
+            ([3.0], 1, 148),
+            ([5.0, 4.0, 0.5], 313, 16)):
+        for strided in (True, False):
+            sched = stationary_schedule(costs, n_tiles, n_slots,
+                                        strided=strided)
+            assert len(sched) == n_slots
+            seen = []
+            for slot in sched:
+                for g, t0, nt in slot:
+                    seen.extend((g, t) for t in range(t0, t0 + nt))
+            assert sorted(seen) == [(g, t) for g in range(len(costs))
+                                    for t in range(n_tiles)]
+            if strided and len(costs) <= n_slots:
+                heavy = [g for g in range(len(costs))
+                         if costs[g] >= 0.25 * max(costs)]
+                for g in heavy:
+                    slots = [i for i, sl in enumerate(sched)
+                             if any(sg[0] == g for sg in sl)]
+                    # contiguous block of slots owned by the group alone
+                    # (light groups may be dealt into them afterwards)
+                    assert slots == list(range(slots[0], slots[-1] + 1))
+                    S = len(slots)
+                    for i, sl in zip(slots, (sched[i] for i in slots)):
+                        tiles = [t for sg in sl if sg[0] == g
+                                 for t in range(sg[1], sg[1] + sg[2])]
+                        assert tiles == list(range(i - slots[0], n_tiles, S))
+
+
+def test_row_stationary_module_compiles_for_sm100a():
+    """Compile-only (no GPU): the automatic choice at the 10-link pendulum is
+    the row-stationary kernel -- one group per dynamic equation, the eleven
+    ``x' = v`` rows as constant runs -- within 227 KB of shared memory and 255
+    registers without spilling; its SASS holds TMA tile loads / stores and the
+    bulk copies of the constant runs; a problem whose input windows do not
+    fit falls back to the grid kernel."""
+    w = workloads.n_link_pendulum(10, 40, seed=7)
+    with tempfile.TemporaryDirectory() as tmp:
+        col = ConstraintCollocator(*w.collocator_args(),
+                                   **w.collocator_kwargs(), tmp_dir=tmp)
+        pm = col.prepare_module()
+        meta = pm.meta
+        assert meta['persistent'] == 2 and meta['warps_per_block'] == 8
+        assert meta['const_rows'] == list(range(11))
+        assert meta['num_groups'] == 11
+        assert [g['rows'] for g in meta['groups']] == \
+            [[j, j + 1] for j in range(11, 22)]
+        assert 0 < meta['smem_bytes'] <= 227 * 1024
+        res = subprocess.run(['cuobjdump', '-res-usage', pm.cubin_path],
+                             capture_output=True, text=True).stdout
+        lines = res.splitlines()
+        line = [lines[i + 1] for i, ln in enumerate(lines)
+                if 'opty_colloc_eval' in ln][0]
+        assert int(re.search(r'REG:(\d+)', line).group(1)) <= 255
+        assert 'LOCAL:0' in line
+        sass = subprocess.run(['cuobjdump', '-sass', pm.cubin_path],
+                              capture_output=True, text=True).stdout
+        assert 'UTMALDG' in sass and 'UTMASTG' in sass and 'UBLKCP' in sass
+        # forcing the grid kernel still works, and so does the fall-back
+        col2 = ConstraintCollocator(
+            *w.collocator_args(), **w.collocator_kwargs(), tmp_dir=tmp,
+            cuda_options={'persistent': False})
+        assert col2.prepare_module().meta['persistent'] == 0
+        col3 = ConstraintCollocator(
+            *w.collocator_args(), **w.collocator_kwargs(), tmp_dir=tmp,
+            cuda_options={'persistent': 'stationary', 'tile_bufs': 2})
+        with pytest.raises(ValueError, match='shared memory'):
+            col3.prepare_module()
+
+
 def test_setup_index_skips_the_symbolic_work_and_tracks_its_inputs():
     """The set-up cache is keyed by the inputs of the symbolic work (discrete
     EOM, symbol layout, options): the same problem comes back from the index

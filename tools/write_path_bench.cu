@@ -66,6 +66,28 @@ __device__ void second_half_tiles(const CUtensorMap* map, double* tile, int gw, 
   }
 }
 
+// all 22 column chunks as tiles; a warp keeps ONE chunk (like an SM that keeps one equation) and walks the
+// node tiles.  shift = 0: the 22 pieces of a node tile are written in the same step by 22 warps;
+// shift > 0: at different steps (chunk c is `shift * c` tiles ahead)
+__device__ void chunk_stationary_tiles(const CUtensorMap* map, double* tile, int gw, int lane, int shift) {
+  const int ntiles = (NODES + 31) / 32, per = M, lanes_per = 53, span = 318;
+  const int c = gw % per, i = gw / per;
+  if (i >= lanes_per) return;
+  for (int k = 0; k * lanes_per < span; ++k) {
+    const int t = (i + k * lanes_per + shift * c) % span;
+    if (t >= ntiles) continue;
+    if (lane == 0) wait_read0();
+    __syncwarp();
+    for (int q = 0; q < P; q += 2) *reinterpret_cast<double2*>(tile + lane * P + q) = make_double2(t, q);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(map, tile, c * P, t * 32);
+      commit();
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256, 1) wk(const __grid_constant__ Maps tm, double* out) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -103,6 +125,9 @@ __global__ void __launch_bounds__(256, 1) wk(const __grid_constant__ Maps tm, do
   if (MODE == 4) second_half_tiles<46>(&tm.w46, tile, gw, nw, lane, 0);
   if (MODE == 5 || MODE == 6) second_half_tiles<46>(&tm.w46, tile, gw, nw, lane, 11);
   if (MODE == 7) second_half_tiles<92>(&tm.w92, tile, gw, nw, lane, 11);
+  if (MODE == 8) chunk_stationary_tiles(&tm.w46, tile, gw, lane, 0);
+  if (MODE == 9) chunk_stationary_tiles(&tm.w46, tile, gw, lane, 14);
+  if (MODE == 10) chunk_stationary_tiles(&tm.w46, tile, gw, lane, 1);
   wait_read0();
 }
 
@@ -166,5 +191,8 @@ int main() {
   run<5>("F bulk copies (first half) + tile stores [32 x 46]", enc, ring, nring, full);
   run<6>("G 16-byte stores (first half) + tile stores [32 x 46]", enc, ring, nring, full);
   run<7>("H bulk copies (first half) + tile stores [32 x 92]", enc, ring, nring, full);
+  run<8>("I chunk-stationary warps, pieces of a node tile in the same step", enc, ring, nring, full);
+  run<9>("J chunk-stationary warps, pieces 14 tiles apart", enc, ring, nring, full);
+  run<10>("K chunk-stationary warps, pieces 1 tile apart", enc, ring, nring, full);
   return 0;
 }
