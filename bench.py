@@ -304,7 +304,8 @@ def config5_strong_scaling(rank, world, local_rank, dist, torch):
     def max_over_ranks(x):
         if dist is None:
             return x
-        t = torch.tensor([x], device='cuda', dtype=torch.float64)
+        t = torch.tensor([x], device=torch.device('cuda', local_rank),
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -398,7 +399,8 @@ def run_own_arm(args, rank, world, local_rank):
         h.eval_device(sync=True)
         per_launch_ms.append(h.last_kernel_ms())
     if dist is not None:
-        t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        t = torch.tensor([ms], device=torch.device('cuda', local_rank),
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * args.steps / (ms * 1e-3)
@@ -443,12 +445,15 @@ def run_own_arm(args, rank, world, local_rank):
             assert con.shape == (prog.M * nn * world,)
             assert jac.shape == (nn * world * prog.K,)
             col_all.close()
+        # (the multi-device collocator made other devices current)
+        torch.cuda.set_device(local_rank)
         barrier()
         e2e_how = ('rank 0 drives all {} GPUs (devices=), full residual and '
                    'Jacobian vectors assembled in one pinned host buffer '
                    'each'.format(world))
     if dist is not None:
-        t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
+        t = torch.tensor([e2e_s], device=torch.device('cuda', local_rank),
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * args.steps / e2e_s

@@ -17,7 +17,14 @@ contains
     trajectory matrix,
 
 ``opty_colloc_eval``
-    the hot kernel: grid = (node tiles, output groups).  A warp owns 32
+    the hot kernel, in one of two skeletons.  Row-stationary persistent
+    kernel (``persistent=2``, the default where a body's input window fits in
+    shared memory): one 8-warp block per SM, one equation row per group, a
+    static schedule (:func:`stationary_schedule`) that keeps a row on the
+    same SMs and makes all rows walk the node tiles at the same pace, the
+    next item's input window prefetched by TMA, rows with node-invariant
+    partials written as constant runs by bulk copies.  Grid kernel
+    (``persistent=0``): grid = (node tiles, output groups).  A warp owns 32
     consecutive collocation nodes (lane = node) of one output group (a
     contiguous range of EOM rows); the block stages the tile's slice of the
     trajectory matrix in shared memory with TMA tile loads, every warp runs
