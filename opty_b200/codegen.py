@@ -632,7 +632,7 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
                 only_groups=None, with_aux=True, pair=None,
                 schedule_options=None, workers=1, persistent=False,
                 num_sms=148, num_nodes=None, blocks_per_sm=1, const_rows=(),
-                const_head_pct=(25, 35, 15), store_hint=0, fused_pre=False,
+                const_head_pct=(35, 50, 15, 70), store_hint=0, fused_pre=False,
                 item_cost=16000, strided_schedule=True, const_pre_pct=0):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block,
@@ -742,10 +742,12 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     w('#define OPTY_NCRUNS {}'.format(len(const_runs)))
     w('#define OPTY_NCONST {}'.format(len(const_entries)))
     chead = list(const_head_pct) if isinstance(
-        const_head_pct, (list, tuple)) else [const_head_pct, 35, 15]
+        const_head_pct, (list, tuple)) else [const_head_pct, 50, 15, 70]
     w('#define OPTY_CONST_HEAD_PCT {}'.format(int(chead[0])))
     w('#define OPTY_CONST_FIRST_PCT {}'.format(int(chead[1])))
     w('#define OPTY_CONST_ITEM_PCT {}'.format(int(chead[2])))
+    w('#define OPTY_CONST_ALIGN_PCT {}'.format(
+        int(chead[3]) if len(chead) > 3 else 100))
     if debug_nostore:
         w('#define OPTY_DEBUG_NOSTORE {}'.format(int(debug_nostore)))
     w('#include "colloc_kernel.cuh"')

@@ -602,11 +602,36 @@ static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void*
 #ifndef OPTY_CONST_ITEM_PCT
 #define OPTY_CONST_ITEM_PCT 15
 #endif
+// Nodes from OPTY_CONST_ALIGN_PCT per cent of the way on are not sent in slices but together with the tiles: the
+// block that has just stored its row's tile of a node tile sends the constant runs of every OPTY_NGROUPS-th
+// node of that tile, so that the two halves of these node rows reach memory at the same time (a DRAM page
+// written in two visits costs two activations; the early slices trade that for the otherwise idle start of
+// the launch).
+#ifndef OPTY_CONST_ALIGN_PCT
+#define OPTY_CONST_ALIGN_PCT 100
+#endif
 #define OPTY_CONST_INIT()                                                                              \
   const int opty_cpre = OPTY_CONST_PRE_NODES(p.n_nodes); /* written by the pre-pass kernel */          \
-  const int opty_cnpw = (p.n_nodes - opty_cpre + OPTY_NSLOTS * OPTY_WARPS - 1) / (OPTY_NSLOTS * OPTY_WARPS); \
+  const int opty_csplit = OPTY_CONST_ALIGN_PCT >= 100                                                  \
+                              ? p.n_nodes                                                              \
+                              : max(opty_cpre, (int)((long long)p.n_nodes * OPTY_CONST_ALIGN_PCT / 100) / OPTY_THREADS * OPTY_THREADS); \
+  const int opty_cnpw = (opty_csplit - opty_cpre + OPTY_NSLOTS * OPTY_WARPS - 1) / (OPTY_NSLOTS * OPTY_WARPS); \
   int opty_cn = opty_cpre + (opty_slot * OPTY_WARPS + (int)(threadIdx.x >> 5)) * opty_cnpw;            \
-  const int opty_ce = min(p.n_nodes, opty_cn + opty_cnpw);
+  const int opty_ce = min(opty_csplit, opty_cn + opty_cnpw);
+// after the tile store of item (opty_g, tile): lane l sends node ctx.node + l - 1 .. (lane 0 sends nothing: it
+// waits on its own store groups), lane 1 also the warp's last node
+#define OPTY_CONST_ALIGNED()                                                                           \
+  if ((OPTY_DEBUG_NOSTORE & 1) == 0 && OPTY_CONST_ALIGN_PCT < 100 && tile_node0 >= opty_csplit) {      \
+    const int l_ = threadIdx.x & 31;                                                                   \
+    for (int q_ = 0; q_ < 2; ++q_) {                                                                   \
+      const int n_ = ctx.node + (q_ == 0 ? l_ - 1 : 31);                                               \
+      if (l_ >= 1 && (q_ == 0 || l_ == 1) && n_ < p.n_nodes && (n_ % OPTY_NGROUPS) == opty_g)          \
+        for (int r_ = 0; r_ < OPTY_NCRUNS; ++r_)                                                       \
+          opty_bulk_store_1d(p.jac + (long long)n_ * OPTY_K + opty_crun[r_][0], opty_cbuf + opty_crun[r_][2], \
+                             (uint32_t)opty_crun[r_][1] * 16u);                                        \
+    }                                                                                                  \
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");                                          \
+  }
 // the next `pct` per cent of the warp's nodes (everything that is left if `all`)
 #define OPTY_CONST_SLICE(pct, all)                                                                     \
   if ((OPTY_DEBUG_NOSTORE & 1) == 0 && opty_cn < opty_ce) {                                            \
@@ -625,6 +650,7 @@ static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void*
 #define OPTY_CONST_FILL()
 #define OPTY_CONST_INIT()
 #define OPTY_CONST_SLICE(pct, all)
+#define OPTY_CONST_ALIGNED()
 #endif
 
 #define OPTY_KERNEL_BEGIN()                                                                              \
@@ -699,6 +725,7 @@ static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void*
     if (ctx.node < p.n_nodes) {
 
 #define OPTY_KERNEL_END()                                                                              \
+      OPTY_CONST_ALIGNED()                                                                             \
     }                                                                                                  \
     OPTY_TIMING_STAMP(2 + 2 * opty_it)                                                                 \
     opty_flip ^= opty_group_odd[opty_g];                                                               \

@@ -122,10 +122,14 @@ DEFAULT_CUDA_OPTIONS = {
                                 # 1 evict_first (the output is read by nobody
                                 # on the device; code and trajectory stay in
                                 # L2), 2 evict_last
-    'const_head_pct': (25, 35, 15),  # per cent of its constant runs a warp
+    'const_head_pct': (35, 50, 15, 70),  # constant runs of the row-stationary
+                                # kernel: per cent of its early nodes a warp
                                 # sends when the block starts / when its first
                                 # input has arrived / with every later item
-                                # (the rest after its last item)
+                                # (the rest after its last item); nodes from
+                                # the 4th figure (per cent of all nodes) on
+                                # are sent together with the tiles of their
+                                # node tile instead
     'use_sympy_cse': True,
     'd2h_skip_constants': True,  # do not re-copy literal Jacobian columns
     'prefetch_jacobian': True,  # constraints() starts the Jacobian D2H early

@@ -1,17 +1,17 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 2400 python -m pytest tests -m gpu -q -s > gpurun_out/r03m_gpu_tests.log 2>&1; echo "gpu tests rc=$?"
-tail -4 gpurun_out/r03m_gpu_tests.log
-timeout 400 python tools/sweep.py run > gpurun_out/r03m_sweep.log 2>&1; cat gpurun_out/r03m_sweep.log
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r03m_bench.json 2> gpurun_out/r03m_bench.err; echo "bench rc=$?"
-timeout 600 python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-config5 > gpurun_out/r03m_bench_steps200.json 2>> gpurun_out/r03m_bench.err
-timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r03m_bench_ref.json 2> gpurun_out/r03m_bench_ref.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r03m_launches_bench.csv python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-config5 > gpurun_out/r03m_bench_under_ncu.log 2>&1
-python tools/launch_summary.py gpurun_out/r03m_launches_bench.csv
-OPTY_REPS=14 OPTY_OPTS='{}' timeout 600 ncu --set full --clock-control none --cache-control none --import-source on -k regex:opty_colloc_eval -s 9 -c 1 -f -o gpurun_out/r03m_cfg2 python tools/profile_one.py > gpurun_out/r03m_cfg2_ncu.log 2>&1
-ncu -i gpurun_out/r03m_cfg2.ncu-rep --page raw --csv > gpurun_out/r03m_cfg2_raw.csv 2>/dev/null
-ncu -i gpurun_out/r03m_cfg2.ncu-rep --page source --csv > gpurun_out/r03m_cfg2_source.csv 2>/dev/null
-python tools/ncu_stalls.py gpurun_out/r03m_cfg2_source.csv > gpurun_out/r03m_cfg2_stalls.txt 2>&1
-rm -f gpurun_out/r03m_cfg2_source.csv gpurun_out/r03m_cfg2.ncu-rep
-cut -c1-900 gpurun_out/r03m_bench.json
+timeout 2400 python -m pytest tests -m gpu -q -s > gpurun_out/r03r_gpu_tests.log 2>&1; echo "gpu tests rc=$?"
+tail -4 gpurun_out/r03r_gpu_tests.log
+timeout 400 python tools/sweep.py run > gpurun_out/r03r_sweep.log 2>&1; cat gpurun_out/r03r_sweep.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r03r_bench.json 2> gpurun_out/r03r_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-config5 > gpurun_out/r03r_bench_steps200.json 2>> gpurun_out/r03r_bench.err
+timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r03r_bench_ref.json 2> gpurun_out/r03r_bench_ref.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r03r_launches_bench.csv python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-config5 > gpurun_out/r03r_bench_under_ncu.log 2>&1
+python tools/launch_summary.py gpurun_out/r03r_launches_bench.csv
+OPTY_REPS=14 OPTY_OPTS='{}' timeout 600 ncu --set full --clock-control none --cache-control none --import-source on -k regex:opty_colloc_eval -s 9 -c 1 -f -o gpurun_out/r03r_cfg2 python tools/profile_one.py > gpurun_out/r03r_cfg2_ncu.log 2>&1
+ncu -i gpurun_out/r03r_cfg2.ncu-rep --page raw --csv > gpurun_out/r03r_cfg2_raw.csv 2>/dev/null
+ncu -i gpurun_out/r03r_cfg2.ncu-rep --page source --csv > gpurun_out/r03r_cfg2_source.csv 2>/dev/null
+python tools/ncu_stalls.py gpurun_out/r03r_cfg2_source.csv > gpurun_out/r03r_cfg2_stalls.txt 2>&1
+rm -f gpurun_out/r03r_cfg2_source.csv gpurun_out/r03r_cfg2.ncu-rep
+cut -c1-900 gpurun_out/r03r_bench.json
