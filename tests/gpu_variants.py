@@ -50,8 +50,12 @@ CONFIG4_VARIANTS = [
     # free parameters and a free time interval (invariants change per call)
     {'persistent': True, 'groups': 4, 'warps_per_block': 4,
      'min_blocks_per_sm': 2},
+    # row-stationary kernel forced onto an odd P: two equations per group,
+    # no constant rows, invariants that change with every call
+    {'persistent': 'stationary', 'tile_bufs': 1},
 ]
-CONFIG4_IDS = ['default', 'narrow_tiles', 'unscheduled', 'persistent']
+CONFIG4_IDS = ['default', 'narrow_tiles', 'unscheduled', 'persistent',
+               'stationary']
 
 # tests/test_gpu_parity.py::test_node_range_shards_reproduce_the_whole
 CONFIG2_SHARD_BOUNDS = [0, 1, 2500, 7001, 9999]

@@ -343,6 +343,39 @@ def test_config4_standin_against_oracle(opts):
     col.close()
 
 
+@pytest.mark.parametrize('links,nodes', [(3, 200), (5, 700)])
+def test_row_stationary_kernel_with_free_parameters_and_interval(links, nodes):
+    """Even P: the automatic choice is the row-stationary kernel, here on
+    backward-Euler problems with several unknown inputs, a known trajectory,
+    unknown parameters and a free time interval (the node-invariant table is
+    re-evaluated with every new free vector); three node tiles at 700 nodes,
+    the last one ragged."""
+    w = workloads.n_link_pendulum_torques(links, nodes)
+    col = _collocator(w)
+    assert col.prepare_module().meta['persistent'] == 2
+    free = w.free(col.num_free)
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    nn, M = _eom_sizes(col)
+    con_f = col.generate_constraint_function()
+    jac_f = col.generate_jacobian_function()
+    P = col._evaluator.program.P
+    f2 = free.copy()
+    f2[-1] *= 1.5
+    f2[-2] += 0.1
+    for point in (free, f2, free):
+        con, jac = con_f(point), np.array(jac_f(point))
+        ocon, ojac = orc.constraints(point), orc.jacobian(point)
+        assert_values_close(con[:M * nn], ocon[:M * nn])
+        assert_values_close(jac[:nn * M * P], ojac[:nn * M * P], row_len=P)
+        np.testing.assert_allclose(con[M * nn:], ocon[M * nn:], rtol=1e-13)
+        np.testing.assert_allclose(jac[nn * M * P:], ojac[nn * M * P:],
+                                   rtol=1e-13)
+    rows, cols = col.jacobian_indices()
+    orows, ocols = orc.jacobian_indices()
+    assert np.array_equal(rows, orows) and np.array_equal(cols, ocols)
+    col.close()
+
+
 # ---------------------------------------------------------------------------
 # boundary behaviour
 # ---------------------------------------------------------------------------
