@@ -321,7 +321,7 @@ def config5_strong_scaling(rank, world, local_rank, dist, torch):
            'device_ms_per_eval': ms, 'algorithmic_GB': B / 1e9,
            'achieved_GBps_aggregate': B / ms / 1e6,
            'evals_per_s': 1e3 / ms}
-    if dist is not None and nnf % world == 0:
+    if dist is not None:
         h.eval_device(sync=True)
         bufs = h.device_buffers()
         dev = torch.device('cuda', local_rank)
@@ -339,6 +339,10 @@ def config5_strong_scaling(rank, world, local_rank, dist, torch):
         ok = bool(torch.equal(full_jac[lo * K:hi * K], jac))
         out.update({
             'nccl_allgather_ms': gather_ms,
+            'allgather_path': 'equal shards: blocks land in the final vector'
+            if nnf % world == 0 else
+            'ragged shards ({} nodes over {} ranks): padded gather + '
+            'concatenation'.format(nnf, world),
             'allgather_busbw_GBps': (full_jac.numel() * 8 / 1e9) *
             (world - 1) / world / (gather_ms * 1e-3),
             'own_block_intact_after_gather': ok})
