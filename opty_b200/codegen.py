@@ -748,6 +748,11 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     w('#define OPTY_CONST_ITEM_PCT {}'.format(int(chead[2])))
     w('#define OPTY_CONST_ALIGN_PCT {}'.format(
         int(chead[3]) if len(chead) > 3 else 100))
+    tick_pct = int(chead[4]) if len(chead) > 4 else 0
+    ticks_per_body = int(chead[5]) if len(chead) > 5 else 3
+    if not (stationary and const_runs):
+        tick_pct = 0
+    w('#define OPTY_CONST_TICK_PCT {}'.format(tick_pct))
     if debug_nostore:
         w('#define OPTY_DEBUG_NOSTORE {}'.format(int(debug_nostore)))
     w('#include "colloc_kernel.cuh"')
@@ -921,6 +926,18 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         w('static __device__ __forceinline__ void opty_group_{}('
           'const OptyCtx& ctx)'.format(g))
         w('{')
+        if tick_pct > 0 and len(lines) > 8 * ticks_per_body:
+            # a trickle of constant runs: ticks at even distances, in front
+            # of a definition (never inside a flush sequence)
+            marks = [len(lines) * (k + 1) // (ticks_per_body + 1)
+                     for k in range(ticks_per_body)]
+            lines = list(lines)
+            for m in reversed(marks):
+                while m < len(lines) and not (
+                        lines[m].startswith('const double') or
+                        lines[m].startswith('double ')):
+                    m += 1
+                lines.insert(m, 'OPTY_TICK();')
         for line in lines:
             w('  ' + line)
         w('}')

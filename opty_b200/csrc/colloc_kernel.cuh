@@ -91,6 +91,9 @@ struct OptyCtx {
   double* tile0;     // the warp's staging buffer 0 (buffer b: + b * OPTY_TILE_DOUBLES)
 #if OPTY_PERSISTENT == 2
   double* tile1;     // staging buffer 1 (the two swap after an item with an odd number of phases)
+  int* cn;           // constant runs: next node of this warp's early share, end of the share, nodes per
+  int ce, ctick;     // OPTY_TICK(), the block's copy of the runs in shared memory
+  const double* cbuf;
 #endif
   double* jac;       // p.jac
   const OptyTmaps* tm;
@@ -610,6 +613,11 @@ static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void*
 #ifndef OPTY_CONST_ALIGN_PCT
 #define OPTY_CONST_ALIGN_PCT 100
 #endif
+#define OPTY_CTX_CONST()                                                \
+  ctx.cn = &opty_cn;                                                    \
+  ctx.ce = opty_ce;                                                     \
+  ctx.ctick = (opty_cnpw * OPTY_CONST_TICK_PCT + 99) / 100;             \
+  ctx.cbuf = opty_cbuf;
 #define OPTY_CONST_INIT()                                                                              \
   const int opty_cpre = OPTY_CONST_PRE_NODES(p.n_nodes); /* written by the pre-pass kernel */          \
   const int opty_csplit = OPTY_CONST_ALIGN_PCT >= 100                                                  \
@@ -618,6 +626,24 @@ static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void*
   const int opty_cnpw = (opty_csplit - opty_cpre + OPTY_NSLOTS * OPTY_WARPS - 1) / (OPTY_NSLOTS * OPTY_WARPS); \
   int opty_cn = opty_cpre + (opty_slot * OPTY_WARPS + (int)(threadIdx.x >> 5)) * opty_cnpw;            \
   const int opty_ce = min(opty_csplit, opty_cn + opty_cnpw);
+// inside a body (the emitter places a few of these per body): the next ctx.ctick nodes of the early share --
+// a trickle that never piles up in front of a tile store
+#ifndef OPTY_CONST_TICK_PCT
+#define OPTY_CONST_TICK_PCT 0
+#endif
+#define OPTY_TICK()                                                                                    \
+  do {                                                                                                 \
+    if ((OPTY_DEBUG_NOSTORE & 1) == 0 && OPTY_CONST_TICK_PCT > 0 && *ctx.cn < ctx.ce) {                \
+      const int n1_ = min(ctx.ce, *ctx.cn + ctx.ctick);                                                \
+      if (ctx.lane >= 1)                                                                               \
+        for (int n_ = *ctx.cn + ctx.lane - 1; n_ < n1_; n_ += 31)                                      \
+          for (int r_ = 0; r_ < OPTY_NCRUNS; ++r_)                                                     \
+            opty_bulk_store_1d(ctx.jac + (long long)n_ * OPTY_K + opty_crun[r_][0], ctx.cbuf + opty_crun[r_][2], \
+                               (uint32_t)opty_crun[r_][1] * 16u);                                      \
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");                                        \
+      *ctx.cn = n1_;                                                                                   \
+    }                                                                                                  \
+  } while (0)
 // after the tile store of item (opty_g, tile): lane l sends node ctx.node + l - 1 .. (lane 0 sends nothing: it
 // waits on its own store groups), lane 1 also the warp's last node
 #define OPTY_CONST_ALIGNED()                                                                           \
@@ -651,6 +677,8 @@ static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void*
 #define OPTY_CONST_INIT()
 #define OPTY_CONST_SLICE(pct, all)
 #define OPTY_CONST_ALIGNED()
+#define OPTY_TICK()
+#define OPTY_CTX_CONST()
 #endif
 
 #define OPTY_KERNEL_BEGIN()                                                                              \
@@ -722,6 +750,7 @@ static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void*
     ctx.node = tile_node0 + (threadIdx.x & ~31);                                                         \
     ctx.active = (tile_node0 + (int)threadIdx.x) < p.n_nodes;                                            \
     ctx.con = p.con + tile_node0 + threadIdx.x;                                                          \
+    OPTY_CTX_CONST()                                                                                     \
     if (ctx.node < p.n_nodes) {
 
 #define OPTY_KERNEL_END()                                                                              \
