@@ -47,14 +47,14 @@ import os
 
 from . import ir, schedule
 
-EMITTER_VERSION = 7
+EMITTER_VERSION = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 KERNEL_HEADER = os.path.join(_HERE, 'csrc', 'colloc_kernel.cuh')
 
 # layout of ``opty_module_info`` (mirrored in csrc/runtime.cu)
 INFO_MAGIC = 0x4f505459   # 'OPTY'
-INFO_WORDS = 32
+INFO_WORDS = 40
 MAX_MAPS = 8
 
 PLAIN_LIVE_LIMIT = 120
@@ -633,7 +633,8 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
                 schedule_options=None, workers=1, persistent=False,
                 num_sms=148, num_nodes=None, blocks_per_sm=1, const_rows=(),
                 const_head_pct=(35, 50, 15, 70), store_hint=0, fused_pre=False,
-                item_cost=16000, strided_schedule=True, const_pre_pct=0):
+                item_cost=16000, strided_schedule=True, const_pre_pct=0,
+                tile_major=False, const_kernel=False):
     """Returns ``(source_text, meta)`` for ``prog`` split into ``groups``
     (list of ``(c0, c1)`` column ranges of the flattened ``M*P`` node block,
     whole equations each; a group also owns the residuals of its rows).
@@ -681,9 +682,11 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         else:
             const_runs.append([j * P, P, len(const_entries)])
         const_entries.extend(prog.jac[j])
-    if const_rows and not (stationary and P % 2 == 0):
-        raise ValueError('constant rows need the row-stationary kernel and '
-                         'an even number of partials per equation')
+    if const_rows and not (tma_store and P % 2 == 0):
+        raise ValueError('constant rows need TMA stores and an even number '
+                         'of partials per equation')
+    if const_rows and not stationary and len(const_entries) * 8 > 200 * 1024:
+        raise ValueError('the constant runs do not fit in shared memory')
     cval0 = ninv + (ninv & 1)
     if const_rows:
         ninv = cval0 + len(const_entries)
@@ -714,7 +717,9 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     w('#define OPTY_D {}'.format(D))
     w('#define OPTY_TILE_DOUBLES {}'.format(32 * C))
     w('#define OPTY_NGROUPS {}'.format(g1 - g0))
-    w('#define OPTY_NINV {}'.format(max(ninv, 1)))
+    # (the constant table holds the invariants the bodies read, not the
+    # constant column runs behind them)
+    w('#define OPTY_NINV {}'.format(max(cval0 if const_rows else ninv, 1)))
     w('#define OPTY_NUNI {}'.format(max(prog.num_uniform, 1)))
     w('#define OPTY_WARPS {}'.format(warps_per_block))
     w('#define OPTY_MIN_BLOCKS {}'.format(min_blocks_per_sm))
@@ -722,6 +727,8 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
     w('#define OPTY_TMA_STORE {}'.format(1 if tma_store else 0))
     w('#define OPTY_NBUF {}'.format(tile_bufs))
     w('#define OPTY_STORE_HINT {}'.format(int(store_hint)))
+    if tile_major and not persistent:
+        w('#define OPTY_TILE_MAJOR 1')
     vol = opts['volatile_loads']
     if vol == 'auto':
         stop_set = set(derived) or None
@@ -741,6 +748,11 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         (8 if (const_rows and with_aux and int(const_pre_pct) > 0) else 0)))
     w('#define OPTY_NCRUNS {}'.format(len(const_runs)))
     w('#define OPTY_NCONST {}'.format(len(const_entries)))
+    if const_runs and not stationary and not const_kernel:
+        # the grid kernel's blocks send the runs themselves
+        w('#define OPTY_GRID_CONST 1')
+        w('#define OPTY_G0 {}'.format(g0))
+        w('#define OPTY_NGROUPS_ALL {}'.format(len(groups)))
     chead = list(const_head_pct) if isinstance(
         const_head_pct, (list, tuple)) else [const_head_pct, 50, 15, 70]
     w('#define OPTY_CONST_HEAD_PCT {}'.format(int(chead[0])))
@@ -841,6 +853,13 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         w('  }')
         w('}')
         w('')
+        if const_runs and not stationary and const_kernel:
+            w('extern "C" __global__ void __launch_bounds__(256)')
+            w('opty_colloc_const(const OptyParams p)')
+            w('{')
+            w('  OPTY_CONST_KERNEL_BODY()')
+            w('}')
+            w('')
         if fused_pre:
             # the same cases as a device function: phase 0 of the
             # row-stationary kernel (one case per block)
@@ -1047,6 +1066,10 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
         info[29] = cval0 if const_rows else 0
         info[30] = 1 if fused_pre else 0
         info[31] = xrows_max
+    if const_runs:
+        info[29] = cval0
+        info[32] = len(const_entries)
+        info[33] = 1 if (const_kernel and not stationary) else 0
     w('extern "C" __device__ const int opty_module_info[{}] = {{{}}};'.format(
         INFO_WORDS, ', '.join(str(v) for v in info)))
     w('')

@@ -173,6 +173,43 @@ static __device__ __forceinline__ void opty_tma_store_2d(const CUtensorMap* map,
 #endif
 }
 
+// 1-D bulk copy shared -> global (constant column runs)
+static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
+#if OPTY_STORE_HINT
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+               "r"(opty_smem_u32(src)), "r"(bytes), "l"(OPTY_STORE_POLICY)
+               : "memory");
+#else
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(opty_smem_u32(src)),
+               "r"(bytes)
+               : "memory");
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// constant rows with the grid kernel: `opty_colloc_const`
+// ---------------------------------------------------------------------------
+// Equations whose partials are all literals or node-invariant values (x' = v and the like: half of the
+// Jacobian of a mechanical system in first-order form) are not output groups.  Their part of every node's
+// Jacobian row is the same run of numbers (values p.cvals, filled by the invariants kernel; runs opty_crun):
+// a persistent grid of 256-thread blocks keeps one copy in shared memory and every thread sends the runs of
+// its nodes with bulk copies of at most 16 KB.  (The row-stationary kernel sends them itself, in slices.)
+#define OPTY_CONST_KERNEL_BODY()                                                                          \
+  extern __shared__ __align__(128) unsigned char opty_smem[];                                             \
+  double* cbuf_ = reinterpret_cast<double*>(opty_smem);                                                   \
+  for (int i_ = threadIdx.x; i_ < OPTY_NCONST; i_ += blockDim.x) cbuf_[i_] = p.cvals[i_];                 \
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                            \
+  __syncthreads();                                                                                        \
+  for (int n_ = blockIdx.x * blockDim.x + threadIdx.x; n_ < p.n_nodes; n_ += gridDim.x * blockDim.x)      \
+    for (int r_ = 0; r_ < OPTY_NCRUNS; ++r_) {                                                            \
+      const int len_ = opty_crun[r_][1] * 2; /* doubles */                                                \
+      for (int o_ = 0; o_ < len_; o_ += 2048)                                                             \
+        opty_bulk_store_1d(p.jac + (long long)n_ * OPTY_K + opty_crun[r_][0] + o_, cbuf_ + opty_crun[r_][2] + o_, \
+                           (uint32_t)min(2048, len_ - o_) * 8u);                                          \
+    }                                                                                                     \
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");                                               \
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+
 // ---------------------------------------------------------------------------
 // main kernel: operand and output macros used by the generated group bodies
 // ---------------------------------------------------------------------------
@@ -409,12 +446,49 @@ static __device__ __forceinline__ double opty_ldin(uint32_t a) {
 //
 // The generated kernel body sits between OPTY_KERNEL_BEGIN and OPTY_KERNEL_END
 // and dispatches on `opty_g`.
+// OPTY_TILE_MAJOR: consecutive blocks (the hardware deals them out in the order x fastest, then y) are the
+// groups of ONE node tile instead of the node tiles of one group, so that the pieces of a node's Jacobian
+// row are written at about the same time (a DRAM page written in several visits costs several activations,
+// tools/write_path_bench.cu variants I/J)
+#ifndef OPTY_TILE_MAJOR
+#define OPTY_TILE_MAJOR 0
+#endif
+#if OPTY_TILE_MAJOR
+#define OPTY_BLOCK_TO_WORK()                                                   \
+  const unsigned opty_lin = blockIdx.y * gridDim.x + blockIdx.x;               \
+  const int opty_g = opty_group_order[opty_lin % OPTY_NGROUPS];                \
+  const int tile_node0 = (int)(opty_lin / OPTY_NGROUPS) * OPTY_THREADS;
+#else
 #define OPTY_BLOCK_TO_WORK()                         \
   const int opty_g = opty_group_order[blockIdx.y];   \
   const int tile_node0 = blockIdx.x * OPTY_THREADS;
+#endif
+// Constant rows with the grid kernel (OPTY_GRID_CONST): the block of (node tile, group g) first sends the
+// constant column runs of every OPTY_NGROUPS_ALL-th node of its tile -- plain streaming stores, threads =
+// consecutive 16-byte pieces of a run, values from the tail of the invariants table in L2 -- so that they
+// drain while the body runs and reach memory together with the tile's other pieces.
+#ifndef OPTY_GRID_CONST
+#define OPTY_GRID_CONST 0
+#endif
+#if OPTY_GRID_CONST && OPTY_NCRUNS > 0
+#define OPTY_GRID_CONST_SHARE()                                                                        \
+  if ((OPTY_DEBUG_NOSTORE & 1) == 0) {                                                                 \
+    const int last_ = min(tile_node0 + OPTY_THREADS, p.n_nodes);                                       \
+    int n_ = tile_node0 + ((OPTY_G0 + opty_g) - tile_node0 % OPTY_NGROUPS_ALL + OPTY_NGROUPS_ALL) % OPTY_NGROUPS_ALL; \
+    for (; n_ < last_; n_ += OPTY_NGROUPS_ALL)                                                         \
+      for (int r_ = 0; r_ < OPTY_NCRUNS; ++r_) {                                                       \
+        const double2* v_ = reinterpret_cast<const double2*>(p.cvals + opty_crun[r_][2]);              \
+        double2* d_ = reinterpret_cast<double2*>(p.jac + (long long)n_ * OPTY_K + opty_crun[r_][0]);   \
+        for (int k_ = threadIdx.x; k_ < opty_crun[r_][1]; k_ += OPTY_THREADS) __stcs(d_ + k_, __ldg(v_ + k_)); \
+      }                                                                                                \
+  }
+#else
+#define OPTY_GRID_CONST_SHARE()
+#endif
 #define OPTY_KERNEL_BEGIN()                          \
   OPTY_SMEM_SETUP()                                  \
   OPTY_BLOCK_TO_WORK()                               \
+  OPTY_GRID_CONST_SHARE()                            \
   OPTY_STAGE_INIT()                                  \
   OPTY_STAGE_INPUT()                                 \
   OPTY_CTX_SETUP()                                   \
@@ -573,17 +647,6 @@ static __device__ __forceinline__ unsigned long long opty_gtime() {
 // profiles/r02s_*.)
 #if OPTY_NCRUNS > 0
 #define OPTY_SMEM_CONST_BYTES ((OPTY_NCONST * 8 + 127) / 128 * 128)
-static __device__ __forceinline__ void opty_bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
-#if OPTY_STORE_HINT
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
-               "r"(opty_smem_u32(src)), "r"(bytes), "l"(OPTY_STORE_POLICY)
-               : "memory");
-#else
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(opty_smem_u32(src)),
-               "r"(bytes)
-               : "memory");
-#endif
-}
 #define OPTY_CONST_FILL()                                                                                      \
   double* opty_cbuf = reinterpret_cast<double*>(opty_smem + OPTY_SMEM_TILES_BYTES + OPTY_SMEM_XIN_BYTES + 128); \
   for (int i_ = threadIdx.x; i_ < OPTY_NCONST; i_ += OPTY_THREADS) opty_cbuf[i_] = p.cvals[i_];                \
@@ -864,6 +927,7 @@ static __device__ __noinline__ int2 opty_steal(const OptyParams& p, const int* o
 #define GB(r) __ldcg(xg + (long long)(r) * p.ldt + 1)
 #if OPTY_TMA_LOAD == 2
 #define OPTY_DRV(d, val) drv[(d) * OPTY_TW] = (val)
+#define OPTY_PCON(j, val) p.con[(long long)(j) * p.ldc + node] = (val)
 #define OPTY_PRE_BEGIN()                                                                              \
   const int node = blockIdx.x * OPTY_PRE_THREADS + threadIdx.x;                                       \
   const int opty_pg = blockIdx.y;                                                                     \

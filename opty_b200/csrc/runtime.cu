@@ -246,10 +246,12 @@ enum {
   INFO_CVAL0 = 29,       //   first entry of the invariants table that belongs to the constant column runs
   INFO_FUSED_PRE = 30,   //   1: the main kernel does the pre-pass's work itself (no pre-pass launch)
   INFO_XROWS = 31,       //   rows of the input window a block fetches per item (box height of the input map)
-  INFO_WORDS = 32
+  INFO_NCONST = 32,      // doubles in the constant column runs
+  INFO_CONST_KERNEL = 33,  // 1: the module has opty_colloc_const, which writes them (else the main kernels do)
+  INFO_WORDS = 40
 };
 const int kInfoMagic = 0x4f505459;
-const int kEmitterVersion = 7;
+const int kEmitterVersion = 8;
 const int kMaxMaps = 8;
 
 }  // namespace
@@ -267,7 +269,7 @@ struct opty_colloc {
 
   // kernel geometry, read from the primary module
   int warps = 0, num_derived = 0, pre_groups = 0, tma_load = 0, tma_store = 0, tile_bufs = 0,
-      tile_doubles = 0, num_inv = 0, persistent = 0, stat_smem = 0, stat_slots = 0, stat_tiles = 0, stat_cval0 = 0, fused_pre = 0, stat_xrows = 0;
+      tile_doubles = 0, num_inv = 0, persistent = 0, stat_smem = 0, stat_slots = 0, stat_tiles = 0, stat_cval0 = 0, fused_pre = 0, stat_xrows = 0, num_const = 0, const_kernel = 0;
 
   struct Module {
     CUmodule mod = nullptr;
@@ -284,6 +286,7 @@ struct opty_colloc {
   std::vector<Module> modules;  // [0] = primary (carries opty_colloc_inv / opty_colloc_pre)
   CUfunction f_inv = nullptr;
   CUfunction f_pre = nullptr;
+  CUfunction f_const = nullptr;  // grid kernel: writes the constant column runs (opty_colloc_const)
   int num_sms = 0;
 
   cudaStream_t stream = nullptr;
@@ -414,6 +417,9 @@ int load_module(opty_colloc* h, const void* cubin, bool primary) {
     h->stat_cval0 = info[INFO_CVAL0];
     h->fused_pre = info[INFO_FUSED_PRE];
     h->stat_xrows = info[INFO_XROWS];
+    h->num_const = info[INFO_NCONST];
+    if (h->num_const > 0) h->stat_cval0 = info[INFO_CVAL0];
+    h->const_kernel = info[INFO_CONST_KERNEL];
     if (h->persistent == 2 && (h->stat_smem < 1 || h->stat_slots < 1 || h->stat_tiles < 1 || h->stat_xrows < 1 ||
                                h->stat_xrows > 256))
       return bail(fail(OPTY_ERR_ARG, "invalid row-stationary geometry in the module info table"));
@@ -440,10 +446,17 @@ int load_module(opty_colloc* h, const void* cubin, bool primary) {
   size_t ci_bytes = 0;
   CUresult r2 = r1 == CUDA_SUCCESS ? g_drv.ModuleGetGlobal(&m.ci_sym, &ci_bytes, m.mod, "opty_ci") : r1;
   if (r2 != CUDA_SUCCESS) return bail(fail(OPTY_ERR_CUDA, "module lacks opty_colloc_eval / opty_ci: " + drv_err(r2)));
-  if (ci_bytes < (size_t)h->num_inv * 8) return bail(fail(OPTY_ERR_ARG, "module's invariant table is too small"));
+  // (the values of the constant column runs sit behind the invariants in d_inv and are read from there)
+  const size_t ci_count = h->num_const > 0 ? (size_t)h->stat_cval0 : (size_t)h->num_inv;
+  if (ci_bytes < ci_count * 8) return bail(fail(OPTY_ERR_ARG, "module's invariant table is too small"));
   if (primary) {
     CUresult r3 = g_drv.ModuleGetFunction(&h->f_inv, m.mod, "opty_colloc_inv");
     if (r3 == CUDA_SUCCESS) r3 = g_drv.ModuleGetFunction(&h->f_pre, m.mod, "opty_colloc_pre");
+    if (r3 == CUDA_SUCCESS && h->num_const > 0 && h->const_kernel) {
+      r3 = g_drv.ModuleGetFunction(&h->f_const, m.mod, "opty_colloc_const");
+      if (r3 == CUDA_SUCCESS)
+        r3 = g_drv.FuncSetAttribute(h->f_const, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, h->num_const * 8);
+    }
     if (r3 != CUDA_SUCCESS) return bail(fail(OPTY_ERR_CUDA, "module lacks the invariants / pre-pass kernels: " + drv_err(r3)));
   }
   h->modules.push_back(std::move(m));
@@ -502,8 +515,10 @@ int launch_eval(opty_colloc* h, bool record_events = false) {
     DRV_CHECK(g_drv.LaunchKernel(h->f_inv, 1, 1, 1, 32, 1, 1, 0, (CUstream)h->stream, args, nullptr));
     h->launches++;
     for (auto& m : h->modules)
-      RT_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(m.ci_sym), h->d_inv, (size_t)h->num_inv * 8,
-                               cudaMemcpyDeviceToDevice, h->stream));
+      if (h->num_const == 0 || h->stat_cval0 > 0)
+        RT_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(m.ci_sym), h->d_inv,
+                                 (size_t)(h->num_const > 0 ? h->stat_cval0 : h->num_inv) * 8,
+                                 cudaMemcpyDeviceToDevice, h->stream));
   }
   h->inv_dirty = false;
   h->ring = (h->ring + 1) % c.out_ring;
@@ -535,6 +550,14 @@ int launch_eval(opty_colloc* h, bool record_events = false) {
                                    (CUstream)h->stream, pargs, nullptr));
       h->launches++;
     }
+  }
+  if (h->f_const) {
+    // constant column runs (grid kernel): one persistent wave of 256-thread blocks, bulk copies from a copy of
+    // the runs in shared memory
+    void* cargs[1] = {&p};
+    DRV_CHECK(g_drv.LaunchKernel(h->f_const, (unsigned)h->num_sms, 1, 1, 256, 1, 1, (unsigned)h->num_const * 8u,
+                                 (CUstream)h->stream, cargs, nullptr));
+    h->launches++;
   }
   for (auto& m : h->modules) {
     p.work = m.d_work;

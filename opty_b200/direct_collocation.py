@@ -102,15 +102,29 @@ DEFAULT_CUDA_OPTIONS = {
     'out_ring': 2,              # device output sets to rotate through (2: an
                                 # evaluation at a new point does not wait for
                                 # the speculative Jacobian copy of the last one)
-    'const_rows': True,         # row-stationary kernel: equations whose
-                                # partials are all node-invariant are written
-                                # as constant column runs, not as groups
+    'const_rows': True,         # equations whose partials are all
+                                # node-invariant are written as constant
+                                # column runs, not as groups (True: with the
+                                # row-stationary kernel; 'grid': with the grid
+                                # kernel too)
     'fused_pre': False,         # row-stationary kernel: derived rows and the
                                 # residuals of constant rows as phase 0 of
                                 # the main kernel instead of a pre-pass launch
                                 # (slower: 256 threads per SM cannot hide the
                                 # latency of the sine / cosine chains,
                                 # profiles/r02y_*)
+    'tile_major': 'auto',       # grid kernel: consecutive blocks of a launch
+                                # are the groups of one node tile, so that the
+                                # pieces of a node's Jacobian row are written
+                                # at about the same time ('auto': with 8-warp
+                                # blocks -- 50-link chain 7.5 -> 6.6 ms,
+                                # config-4 stand-in 46.1 -> 42.7 us; with
+                                # 2-warp blocks an SM would host four
+                                # different bodies at a time: 26.9 -> 34.4 us
+                                # at the 10-link pendulum)
+    'const_kernel': False,      # grid kernel with constant rows: a separate
+                                # kernel writes the runs (else the blocks of
+                                # the main kernel do, with their tiles)
     'const_pre_pct': 0,         # per cent of the nodes whose constant runs the
                                 # pre-pass kernel writes (plain stores)
     'strided_schedule': True,   # row-stationary schedule: whole slots per
@@ -728,12 +742,34 @@ def _prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         tma_store))
 
     const_rows = []
-    if stationary and opts['const_rows'] and unit_rows == 1 and tma_store:
+    if opts['const_rows'] and unit_rows == 1 and tma_store and \
+            pair is not None and (stationary or opts['const_rows'] == 'grid'):
+        # (with the grid kernel only on request, 'grid': its blocks then send
+        # the runs of a share of their tile's nodes -- or a separate kernel
+        # does, `const_kernel` -- which measured the same as leaving the rows
+        # to store-only groups at the 50-link chain, 6.4-6.6 ms, and slower at
+        # the 10-link pendulum, profiles/r03z_*, r04b_*)
         kinds = prog.entry_kind()
         const_rows = [j for j in range(M)
                       if max(kinds[j * prog.P:(j + 1) * prog.P]) < 2]
         if len(const_rows) == M:
             const_rows = const_rows[1:]     # the main kernel needs a group
+        if not stationary and len(const_rows) * prog.P * 8 > 200 * 1024:
+            const_rows = []
+
+    def drop_const(rows):
+        # constant rows are not output groups: cut them out of the ranges
+        out = []
+        for r0, r1 in rows:
+            start = None
+            for j in range(r0, r1 + 1):
+                if j < r1 and j not in const_rows:
+                    if start is None:
+                        start = j
+                elif start is not None:
+                    out.append((start, j))
+                    start = None
+        return out
 
     def column_parts(stop=None):
         if stationary and groups >= M // unit_rows:
@@ -761,6 +797,8 @@ def _prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
                     r += step
             if len(cut) <= runtime.OPTY_MAX_GROUPS:
                 rows = cut
+        if const_rows:
+            rows = drop_const(rows)
         return [(r0 * prog.P, r1 * prog.P) for r0, r1 in rows]
 
     parts = column_parts()
@@ -818,6 +856,9 @@ def _prepare_program_module(prog, num_nodes, method, opts, tmp_dir=None,
         item_cost=opts['item_cost'],
         strided_schedule=opts['strided_schedule'],
         const_pre_pct=opts['const_pre_pct'],
+        const_kernel=opts['const_kernel'],
+        tile_major=(wpb >= 8) if opts['tile_major'] == 'auto'
+        else bool(opts['tile_major']),
         schedule_options=sched_opts,
         workers=(os.cpu_count() or 1) if cost >= 20000 else 1)
 

@@ -343,6 +343,48 @@ def test_config4_standin_against_oracle(opts):
     col.close()
 
 
+def test_config4_standin_full_size_against_oracle():
+    """The stand-in of BASELINE config 4 at the size of its scaling runs
+    (8 links, 20 000 backward-Euler nodes: 18 states, 8 unknown inputs, a
+    known trajectory, unknown parameters, a free time interval, instance
+    constraints; 16.9 M Jacobian entries) against the oracle, whole vectors;
+    and its node shards (the strong-scaling decomposition over 8 GPUs, here
+    the first, a middle and the last one on this device) bit for bit against
+    the unsharded evaluation."""
+    from opty_b200.sharding import node_shard
+    w = workloads.n_link_pendulum_torques(8, 20000)
+    col = _collocator(w)
+    free = w.free(col.num_free)
+    orc = OracleCollocator(*w.collocator_args(), **w.collocator_kwargs())
+    con = col.generate_constraint_function()(free)
+    jac = np.array(col.generate_jacobian_function()(free))
+    ocon, ojac = orc.constraints(free), orc.jacobian(free)
+    nn, M = _eom_sizes(col)
+    P = col._evaluator.program.P
+    K = M * P
+    assert len(jac) >= 16_000_000
+    assert_values_close(con[:M * nn], ocon[:M * nn])
+    assert_values_close(jac[:nn * K], ojac[:nn * K], row_len=P)
+    np.testing.assert_allclose(con[M * nn:], ocon[M * nn:], rtol=1e-13)
+    np.testing.assert_allclose(jac[nn * K:], ojac[nn * K:], rtol=1e-13)
+    rows, cols = col.jacobian_indices()
+    orows, ocols = orc.jacobian_indices()
+    assert np.array_equal(rows, orows) and np.array_equal(cols, ocols)
+    opts = {'groups': col._evaluator.meta['num_groups'],
+            'warps_per_block': col._evaluator.meta['warps_per_block'],
+            'min_blocks_per_sm': col._evaluator.meta['min_blocks_per_sm']}
+    for rank in (0, 3, 7):
+        lo, hi = node_shard(20000, rank, 8)
+        part = _collocator(w, node_range=(lo, hi), cuda_options=opts)
+        c = part.generate_constraint_function()(free)
+        j = np.array(part.generate_jacobian_function()(free))
+        assert np.array_equal(c.reshape(M, hi - lo),
+                              con[:M * nn].reshape(M, nn)[:, lo:hi])
+        assert np.array_equal(j, jac[lo * K:hi * K])
+        part.close()
+    col.close()
+
+
 @pytest.mark.parametrize('links,nodes', [(3, 200), (5, 700)])
 def test_row_stationary_kernel_with_free_parameters_and_interval(links, nodes):
     """Even P: the automatic choice is the row-stationary kernel, here on

@@ -17,6 +17,7 @@ from opty_b200 import ConstraintCollocator  # noqa: E402
 LINKS = int(os.environ.get('OPTY_LINKS', 8))
 NODES = int(os.environ.get('OPTY_NODES', 20000))
 VARIANTS = [('grid kernel (default for odd P)', {}),
+            ('grid kernel, tile-major dispatch', {'tile_major': True}),
             ('row-stationary, forced', {'persistent': 'stationary',
                                         'tile_bufs': 1}),
             ('row-stationary, forced, 4 warps',
