@@ -105,7 +105,10 @@ def gather_vectors(local_con, local_jac, num_collocation_nodes, num_eom,
     final vector (``all_gather_into_tensor`` into the result, no staging
     copy) and the eom-major residuals take one gather plus ONE permute
     ``(G, M, nn) -> (M, G*nn)``; ragged shards (``N - 1`` not divisible by
-    the number of ranks) go through a padded gather."""
+    the number of ranks) go through a padded gather and one concatenation
+    (NCCL's own gather of unequal blocks into views of the final vector --
+    one broadcast per rank -- measured slower: 17.2 against 13.5 ms for the
+    8.4 GB of the 50-link chain on two GPUs)."""
     import torch
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
