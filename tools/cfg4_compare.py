@@ -18,6 +18,9 @@ LINKS = int(os.environ.get('OPTY_LINKS', 8))
 NODES = int(os.environ.get('OPTY_NODES', 20000))
 VARIANTS = [('grid kernel (default for odd P)', {}),
             ('grid kernel, tile-major dispatch', {'tile_major': True}),
+            ('grid kernel, 8 groups', {'groups': 8, 'tile_major': False}),
+            ('grid kernel, 8 groups, tile-major', {'groups': 8,
+                                                   'tile_major': True}),
             ('row-stationary, forced', {'persistent': 'stationary',
                                         'tile_bufs': 1}),
             ('row-stationary, forced, 4 warps',
