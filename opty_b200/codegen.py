@@ -77,6 +77,8 @@ SCHEDULE_DEFAULTS = {
                             # operations (they cannot afford the registers a
                             # merged load pins; small bodies gain more from
                             # the shorter instruction stream)
+    'load_ahead': 0,        # input loads are emitted this many statements
+                            # before the schedule's place for them
     'fence_every': 0,       # > 0: a warp-level memory fence after this many
                             # statements.  ptxas hoists global loads far
                             # ahead of their use to overlap their latency;
@@ -387,10 +389,24 @@ class _ScheduledWriter(object):
                 out.append((' + ' if sg > 0 else ' - ') + e)
         return ''.join(out)
 
-    def lines_for(self, layout, fence_every=0):
+    def lines_for(self, layout, fence_every=0, load_ahead=0):
+        lines, num_ops, loads = self._lines_for(layout, fence_every)
+        if load_ahead > 0:
+            # input loads issued `load_ahead` statements before the place the
+            # schedule gave them: with direct input loads (large models) a
+            # load is an L2 access of several hundred cycles that nothing
+            # else in the warp covers
+            for i in loads:
+                j = max(0, i - load_ahead)
+                if j < i:
+                    lines.insert(j, lines.pop(i))
+        return lines, num_ops
+
+    def _lines_for(self, layout, fence_every=0):
         dag = self.dag
         T = self.T
         lines = []
+        loads = []
         slots = layout.slots
         phases = layout.phases
         deferred = self.sched.deferred
@@ -410,6 +426,7 @@ class _ScheduledWriter(object):
                     since_fence = 0
             if kind == schedule.LOAD:
                 v = e[1]
+                loads.append(len(lines))
                 lines.append('const double v{} = {};'.format(v, self.leaf(v)))
             elif kind == schedule.OP:
                 v = e[1]
@@ -471,7 +488,7 @@ class _ScheduledWriter(object):
                     lines.append('OPTY_FLUSH_END()')
         assert all(v == 0 for v in left)
         lines.append('OPTY_DRAIN();')
-        return lines, num_ops
+        return lines, num_ops, loads
 
 
 _INPUT_REF = __import__('re').compile(r'\bX([ABD])\((\d+)\)')
@@ -598,7 +615,8 @@ def _emit_group(g):
         # plain order: slots in layout order (phases are contiguous there)
         sched = plain or schedule.plain_order(prog.tape, layout.roots, stop)
     writer = _ScheduledWriter(prog, _WORK['derived_index'], sched)
-    lines, num_ops = writer.lines_for(layout, int(opts['fence_every']))
+    lines, num_ops = writer.lines_for(layout, int(opts['fence_every']),
+                                      int(opts.get('load_ahead', 0)))
     meta = {'rows': [gc0 // prog.P, gc1 // prog.P], 'cols': [gc0, gc1],
             'col0': gc0, 'ncols': layout.stored, 'ops': sched.num_ops,
             'statements': num_ops, 'peak_live': sched.peak_live,

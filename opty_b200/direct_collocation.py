@@ -96,6 +96,7 @@ DEFAULT_CUDA_OPTIONS = {
     'inline_cost': 2,
     'remat_cost': 24,
     'volatile_loads': 'auto',   # input loads nvcc may not merge (large bodies)
+    'load_ahead': 0,            # input loads this many statements early
     'fence_every': 0,           # warp-level memory fence every so many
                                 # statements (bounds ptxas' load hoisting)
     'debug_nostore': False,     # measurement aid: skip Jacobian tile stores

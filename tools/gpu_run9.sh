@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python tools/sweep.py run > gpurun_out/r04g_sweep.log 2>&1; cat gpurun_out/r04g_sweep.log
+timeout 300 python tools/sweep.py run > gpurun_out/r04i_sweep.log 2>&1; cat gpurun_out/r04i_sweep.log
