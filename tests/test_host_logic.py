@@ -329,7 +329,8 @@ def test_narrow_staging_buffers_and_schedule_options(name, make):
                  {'groups': 3, 'tile_cols': 20, 'reassociate': False,
                   'tile_bufs': 1},
                  {'groups': 2, 'schedule': False, 'tile_cols': 16},
-                 {'groups': 1, 'live_budget': 8, 'remat_cost': 60}):
+                 {'groups': 1, 'live_budget': 8, 'remat_cost': 60},
+                 {'groups': 2, 'load_ahead': 40, 'schedule': True}):
         w = make()      # the seeded free vector continues the workload's rng
         col = ConstraintCollocator(*w.collocator_args(),
                                    **w.collocator_kwargs(), cuda_options=opts)
