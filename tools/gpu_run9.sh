@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python tools/sweep.py run > gpurun_out/r04i_sweep.log 2>&1; cat gpurun_out/r04i_sweep.log
+python tools/e2e_breakdown.py > gpurun_out/r04l_e2e_breakdown.txt 2>&1; cat gpurun_out/r04l_e2e_breakdown.txt | grep -v Warn
