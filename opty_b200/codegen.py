@@ -869,6 +869,7 @@ def emit_module(prog, groups, method, tile_cols='auto', warps_per_block=2,
             w(line)
         w('    default: break;')
         w('  }')
+        w('  OPTY_PRE_END()')
         w('}')
         w('')
         if const_runs and not stationary and const_kernel:

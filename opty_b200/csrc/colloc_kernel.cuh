@@ -922,6 +922,12 @@ static __device__ __noinline__ int2 opty_steal(const OptyParams& p, const int* o
 // own tile and, for the first two columns of a tile, also to the halo slots of
 // the tile before.
 #define OPTY_PRE_THREADS 128
+// last statement of the pre-pass kernel.  The kernel may have been launched with programmatic stream
+// serialisation directly behind the main kernel of the previous evaluation and have started before that
+// kernel's stores were flushed: it reads and writes nothing that kernel touches, but it must not COMPLETE
+// before it -- the next main kernel waits for this grid only and writes output sets whose previous contents
+// have to be final by then.  (No effect after an ordinary launch.)
+#define OPTY_PRE_END() asm volatile("griddepcontrol.wait;" ::: "memory");
 #define OPTY_COPY_ROWS 16
 #define GA(r) __ldcg(xg + (long long)(r) * p.ldt)
 #define GB(r) __ldcg(xg + (long long)(r) * p.ldt + 1)

@@ -546,8 +546,32 @@ int launch_eval(opty_colloc* h, bool record_events = false) {
     if (gy > 0 && !h->fused_pre) {
       pre_launched = getenv("OPTY_B200_NO_PDL") == nullptr;
       void* pargs[1] = {&p};
-      DRV_CHECK(g_drv.LaunchKernel(h->f_pre, (unsigned)((h->nn + 1 + 127) / 128), gy, 1, 128, 1, 1, 0,
-                                   (CUstream)h->stream, pargs, nullptr));
+      if (pre_launched && h->persistent == 2) {
+        // Programmatic serialisation is a permission: behind a copy or an event the launch is ordered as
+        // usual; directly behind the main kernel of the previous evaluation (back-to-back evaluations of a
+        // resident point) the launch overhead overlaps that kernel's tail.  The pre-pass reads nothing that
+        // kernel writes and starts only after its last block has exited (the main kernel never triggers
+        // its dependents early), so it cannot overwrite derived rows that are still being read.
+        CUlaunchConfig lc;
+        memset(&lc, 0, sizeof(lc));
+        lc.gridDimX = (unsigned)((h->nn + 1 + 127) / 128);
+        lc.gridDimY = gy;
+        lc.gridDimZ = 1;
+        lc.blockDimX = 128;
+        lc.blockDimY = lc.blockDimZ = 1;
+        lc.sharedMemBytes = 0;
+        lc.hStream = (CUstream)h->stream;
+        CUlaunchAttribute attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+        attr.value.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = &attr;
+        lc.numAttrs = 1;
+        DRV_CHECK(g_drv.LaunchKernelEx(&lc, h->f_pre, pargs, nullptr));
+      } else {
+        DRV_CHECK(g_drv.LaunchKernel(h->f_pre, (unsigned)((h->nn + 1 + 127) / 128), gy, 1, 128, 1, 1, 0,
+                                     (CUstream)h->stream, pargs, nullptr));
+      }
       h->launches++;
     }
   }

@@ -61,6 +61,7 @@ static inline double opty_sign(double x) { return (double)((x > 0.0) - (x < 0.0)
 
 #define GA(r) xg[(long long)(r) * p.ldt]
 #define GB(r) xg[(long long)(r) * p.ldt + 1]
+#define OPTY_PRE_END()
 #define OPTY_DRV(d, val) drv[(long long)(d) * p.ldt] = (val)
 #define OPTY_PRE_BEGIN() \
   const int node = (int)blockIdx.x; \
